@@ -1,0 +1,696 @@
+// rtb_kernels.cu — the wavefront path tracer's CUDA kernels (sm_100a).
+//
+//   generate    camera rays for one batch of (pixel, sample) paths          Renderer.cu:183-204, cu_Cameras.cuh:27-30,54-64,87-89
+//   traverse    closest hit through the 64-byte two-box BVH nodes           BVH.cu:54-106, aabb.cuh:30-44, SphereHittable.cuh:15-33
+//   shade       material scatter + texture evaluation + queue compaction    Renderer.cu:139-181, cu_materials.cuh:17-144, cu_Textures.cuh:9-40
+//   accumulate  per-pixel sum of the batch's path contributions             Renderer.cu:204-206
+//   resolve     mean -> clamp -> sqrt -> float4                             Renderer.cu:206-216
+//
+// Compiled with -fmad=false: every fused multiply-add below is explicit (see rtmath.h), so the
+// CPU oracle reproduces the geometry bit for bit.  No tensor cores: nothing here is a dense
+// contraction.  All kernels are persistent (grid = SMs x resident blocks) and pull work in
+// warp- or block-sized chunks from a device counter, so the same launch sequence (and the same
+// CUDA graph) serves every bounce regardless of how many paths are still alive.
+#include "rtb_kernels.h"
+
+#include <cfloat>
+
+#include "rtb_types.h"
+#include "rtmath.h"
+
+namespace rtb {
+
+using rt::v3;
+
+#define TRAVERSE_THREADS 128
+#define SHADE_THREADS 256
+#define STREAM_THREADS 256
+#define STACK_SIZE 32
+#define FULL_MASK 0xFFFFFFFFu
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+
+__device__ __forceinline__ v3 xyz(const float4& f) { return rt::mk(f.x, f.y, f.z); }
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// Path id -> (global pixel index, absolute sample index).  Paths of a batch are laid out
+// sample-major: id = local_sample * npix + local_pixel, local pixels row-major from row_begin.
+__device__ __forceinline__ void path_pixel_sample(const BatchParams& bp, uint32_t batch, uint32_t path,
+                                                  uint32_t& pixel, uint32_t& sample) {
+	uint32_t sl = path / bp.npix;
+	uint32_t pl = path - sl * bp.npix;
+	pixel = bp.row_begin * bp.width + pl;
+	sample = bp.sample_begin + batch * bp.samples_per_batch + sl;
+}
+
+__device__ __forceinline__ uint32_t batch_sample_count(const BatchParams& bp, uint32_t batch) {
+	uint64_t s0 = (uint64_t)bp.sample_begin + (uint64_t)batch * bp.samples_per_batch;
+	if (s0 >= bp.sample_end) return 0;
+	uint64_t left = bp.sample_end - s0;
+	return (uint32_t)(left < bp.samples_per_batch ? left : bp.samples_per_batch);
+}
+
+// ------------------------------------------------------------------------------------------------
+// generate
+
+__global__ void __launch_bounds__(STREAM_THREADS)
+generate_kernel(BatchParams bp, rtb_camera cam, WaveView wv) {
+	const uint32_t batch = *wv.batch_index;
+	const uint32_t ns = batch_sample_count(bp, batch);
+	const uint32_t n = ns * bp.npix;
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t stride = gridDim.x * blockDim.x;
+
+	// Reset the per-bounce queue lengths and work counters of this batch.
+	if (blockIdx.x == 0) {
+		for (uint32_t i = threadIdx.x; i <= bp.max_depth; i += blockDim.x) wv.n_live[i] = (i == 0) ? n : 0u;
+		for (uint32_t i = threadIdx.x; i < 2 * (bp.max_depth + 1); i += blockDim.x) wv.work[i] = 0u;
+	}
+
+	const float px = 1.0f / (float)bp.width, py = 1.0f / (float)bp.height;   // pixel_size  Renderer.cu:188
+	for (uint32_t path = tid; path < n; path += stride) {
+		uint32_t pixel, sample;
+		path_pixel_sample(bp, batch, path, pixel, sample);
+		uint32_t y = pixel / bp.width, x = pixel - y * bp.width;
+		rt::f4 r = rt::rng4(bp.seed, pixel, sample, RT_CAMERA_BOUNCE, rt::STREAM_SCATTER);
+		// ndc = (vec2(x,y) + 0.5) * pixel_size * 2 - 1 ; jitter = point in unit disc * pixel_size   Renderer.cu:192,199
+		float ndcx = fmaf(((float)x + 0.5f) * px, 2.0f, -1.0f);
+		float ndcy = fmaf(((float)y + 0.5f) * py, 2.0f, -1.0f);
+		float jx, jy; rt::unit_disc(r.x, r.y, jx, jy);
+		float s = fmaf(jx, px, ndcx), t = fmaf(jy, py, ndcy);
+		v3 o = rt::mk(cam.o[0], cam.o[1], cam.o[2]);
+		v3 cu = rt::mk(cam.u[0], cam.u[1], cam.u[2]), cv = rt::mk(cam.v[0], cam.v[1], cam.v[2]), cw = rt::mk(cam.w[0], cam.w[1], cam.w[2]);
+		v3 d; float time = 0.0f;
+		if (cam.kind == RTB_CAM_DEFOCUS) {
+			// DefocusBlurCamera::sample_ray  cu_Cameras.cuh:54-64
+			rt::f4 l = rt::rng4(bp.seed, pixel, sample, RT_CAMERA_BOUNCE, rt::STREAM_LENS);
+			float lx, ly; rt::unit_disc(l.x, l.y, lx, ly);
+			v3 off = rt::mul(rt::mk(fmaf(cv.x, ly, cu.x * lx), fmaf(cv.y, ly, cu.y * lx), fmaf(cv.z, ly, cu.z * lx)), cam.lens_radius);
+			v3 fwd = rt::mul(cw, cam.focus_dist);
+			v3 hori = rt::mul(rt::mul(cu, cam.viewport_width), cam.focus_dist);
+			v3 vert = rt::mul(rt::mul(cv, cam.viewport_height), cam.focus_dist);
+			d = rt::sub(rt::madd(vert, t, rt::madd(hori, s, fwd)), off);
+			o = rt::add(o, off);
+			time = rt::mixf(cam.t0, cam.t1, r.z);
+		} else {
+			// PinholeCamera / MotionBlurCamera::sample_ray  cu_Cameras.cuh:27-30,87-89
+			d = rt::madd(cv, t, rt::madd(cu, s, cw));
+			if (cam.kind == RTB_CAM_MOTION) time = rt::mixf(cam.t0, cam.t1, r.z);
+		}
+		wv.ray_o[0][path] = make_float4(o.x, o.y, o.z, time);
+		wv.ray_d[0][path] = make_float4(d.x, d.y, d.z, __uint_as_float(path));
+		wv.thr[0][path] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+		wv.contrib[path] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// primitive tests (shared by traverse and the hit-record hook)
+
+// _sphere_closest_intersection  SphereHittable.cuh:15-33 (a = d.d hoisted per ray)
+__device__ __forceinline__ float sphere_closest(v3 o, v3 d, float a, v3 c, float r) {
+	v3 oc = rt::sub(o, c);
+	float hb = rt::dot(d, oc);
+	float cc = fmaf(-r, r, rt::dot(oc, oc));
+	float disc = fmaf(hb, hb, -(a * cc));
+	if (!(disc > 0.0f)) return FLT_MAX;
+	float sq = sqrtf(disc);
+	float t = (-hb - sq) / a;
+	if (t < 0.0f) {
+		t = (-hb + sq) / a;
+		if (t < 0.0f) return FLT_MAX;
+	}
+	return t;
+}
+
+// Book quad::hit / triangle with the reference's t policy (t >= 0, strictly closer than the best).
+__device__ __forceinline__ float planar_hit(v3 o, v3 d, const float4* pp, float4 q0, bool tri, float tbest) {
+	float4 q1 = ldg4(pp + 1), q2 = ldg4(pp + 2), q3 = ldg4(pp + 3);
+	v3 N = rt::mk(q1.w, q2.w, q3.w);
+	float denom = rt::dot(N, d);
+	if (fabsf(denom) < 1e-8f) return FLT_MAX;
+	float t = (q0.w - rt::dot(N, o)) / denom;
+	if (!(t >= 0.0f) || !(t < tbest)) return FLT_MAX;
+	v3 P = rt::madd(d, t, o);
+	v3 planar = rt::sub(P, xyz(q0));
+	v3 w = xyz(q3);
+	float alpha = rt::dot(w, rt::cross(planar, xyz(q2)));
+	float beta = rt::dot(w, rt::cross(xyz(q1), planar));
+	if (tri) { if (alpha < 0.0f || beta < 0.0f || alpha + beta > 1.0f) return FLT_MAX; }
+	else { if (alpha < 0.0f || alpha > 1.0f || beta < 0.0f || beta > 1.0f) return FLT_MAX; }
+	return t;
+}
+
+// constant_medium::hit (book) over a convex boundary interval [t1,t2] found for any-sign t.
+__device__ __forceinline__ float medium_sample(float t1, float t2, float a, float neg_inv_density, float u, float tbest) {
+	if (!(t2 > t1 + 0.0001f)) return FLT_MAX;     // second boundary query: interval(t1 + 0.0001, inf)
+	if (t1 < 0.0f) t1 = 0.0f;                     // ray_t.min (the reference accepts t >= 0)
+	if (t2 > tbest) t2 = tbest;                   // ray_t.max = closest so far
+	if (t1 >= t2) return FLT_MAX;
+	float len = sqrtf(a);
+	float dist_inside = (t2 - t1) * len;
+	float hit_distance = neg_inv_density * rt::logpos(u);
+	if (hit_distance > dist_inside) return FLT_MAX;
+	return t1 + hit_distance / len;
+}
+
+__device__ __forceinline__ float medium_sphere_hit(v3 o, v3 d, float a, float4 q0, float nid, float u, float tbest) {
+	v3 oc = rt::sub(o, xyz(q0));
+	float hb = rt::dot(d, oc);
+	float cc = fmaf(-q0.w, q0.w, rt::dot(oc, oc));
+	float disc = fmaf(hb, hb, -(a * cc));
+	if (!(disc > 0.0f)) return FLT_MAX;
+	float sq = sqrtf(disc);
+	return medium_sample((-hb - sq) / a, (-hb + sq) / a, a, nid, u, tbest);
+}
+
+__device__ __forceinline__ float medium_box_hit(v3 o, v3 d, float a, float4 q0, float4 q1, float4 q2, float u, float tbest) {
+	// world -> object: translate back, rotate by -theta about y (book translate::hit / rotate_y::hit)
+	float cs = q0.w, sn = q1.w;
+	v3 ot = rt::sub(o, xyz(q2));
+	v3 oo = rt::mk(fmaf(cs, ot.x, -(sn * ot.z)), ot.y, fmaf(sn, ot.x, cs * ot.z));
+	v3 dd = rt::mk(fmaf(cs, d.x, -(sn * d.z)), d.y, fmaf(sn, d.x, cs * d.z));
+	float tn = -FLT_MAX, tf = FLT_MAX;
+	const float bmin[3] = {q0.x, q0.y, q0.z}, bmax[3] = {q1.x, q1.y, q1.z};
+	const float oc[3] = {oo.x, oo.y, oo.z}, dc[3] = {dd.x, dd.y, dd.z};
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		if (dc[k] == 0.0f) { if (oc[k] < bmin[k] || oc[k] > bmax[k]) return FLT_MAX; continue; }
+		float ta = (bmin[k] - oc[k]) / dc[k], tb = (bmax[k] - oc[k]) / dc[k];
+		float lo = ta < tb ? ta : tb, hi = ta < tb ? tb : ta;
+		tn = lo > tn ? lo : tn; tf = hi < tf ? hi : tf;
+	}
+	if (!(tn < tf)) return FLT_MAX;
+	return medium_sample(tn, tf, a, q2.w, u, tbest);
+}
+
+// ------------------------------------------------------------------------------------------------
+// traverse
+
+struct MediumRng { uint32_t seed, pixel, sample, bounce; };
+
+template <bool MEDIA>
+__device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float time, const MediumRng& mr,
+                                          int* __restrict__ stack, float& tbest_out, int& code_out) {
+	const float a = rt::dot(d, d);
+	// Slab test with a per-ray reciprocal; an exactly-zero component is nudged so 0 * inf never appears.
+	const float gx = fabsf(d.x) < 1e-20f ? copysignf(1e-20f, d.x) : d.x;
+	const float gy = fabsf(d.y) < 1e-20f ? copysignf(1e-20f, d.y) : d.y;
+	const float gz = fabsf(d.z) < 1e-20f ? copysignf(1e-20f, d.z) : d.z;
+	const float idx = 1.0f / gx, idy = 1.0f / gy, idz = 1.0f / gz;
+	const float oix = -(o.x * idx), oiy = -(o.y * idy), oiz = -(o.z * idz);
+
+	float tbest = FLT_MAX;
+	int best = -1;
+	int cur = sv.root_ref;
+	int sp = 0;
+	for (;;) {
+		if (cur >= 0) {
+			const float4* np = sv.nodes + 4 * (size_t)cur;
+			const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2);
+			const int4 n3 = __ldg(reinterpret_cast<const int4*>(np + 3));
+			float lx0 = fmaf(n0.x, idx, oix), lx1 = fmaf(n0.w, idx, oix);
+			float ly0 = fmaf(n0.y, idy, oiy), ly1 = fmaf(n1.x, idy, oiy);
+			float lz0 = fmaf(n0.z, idz, oiz), lz1 = fmaf(n1.y, idz, oiz);
+			float rx0 = fmaf(n1.z, idx, oix), rx1 = fmaf(n2.y, idx, oix);
+			float ry0 = fmaf(n1.w, idy, oiy), ry1 = fmaf(n2.z, idy, oiy);
+			float rz0 = fmaf(n2.x, idz, oiz), rz1 = fmaf(n2.w, idz, oiz);
+			float ltmin = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fminf(lz0, lz1));
+			float ltmax = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fmaxf(lz0, lz1));
+			float rtmin = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fminf(rz0, rz1));
+			float rtmax = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fmaxf(rz0, rz1));
+			// aabb::intersects: tmin <= tmax && tmin < ray_max && tmax > 0   aabb.cuh:41
+			bool hl = ltmin <= ltmax && ltmin < tbest && ltmax > 0.0f;
+			bool hr = rtmin <= rtmax && rtmin < tbest && rtmax > 0.0f;
+			if (hl && hr) {
+				// nearer child next, farther child on the stack   BVH.cu:91-97
+				bool sw = ltmin > rtmin;
+				int nearc = sw ? n3.y : n3.x, farc = sw ? n3.x : n3.y;
+				stack[sp * TRAVERSE_THREADS] = farc; ++sp;
+				cur = nearc;
+				continue;
+			}
+			if (hl) { cur = n3.x; continue; }
+			if (hr) { cur = n3.y; continue; }
+		} else {
+			const int code = ~cur;
+			const int type = code & 7;
+			const float4* pp = sv.prims + 4 * (size_t)(code >> 3);
+			const float4 q0 = ldg4(pp);
+			float t = FLT_MAX;
+			if (type == PRIM_SPHERE) {
+				t = sphere_closest(o, d, a, xyz(q0), q0.w);
+			} else if (type == PRIM_MOVING_SPHERE) {
+				// center = mix(center0, center1, ray.time)   SphereHittable.cu:92
+				const float4 q1 = ldg4(pp + 1);
+				t = sphere_closest(o, d, a, rt::mix(xyz(q0), xyz(q1), time), q0.w);
+			} else if (type == PRIM_QUAD || type == PRIM_TRIANGLE) {
+				t = planar_hit(o, d, pp, q0, type == PRIM_TRIANGLE, tbest);
+			} else if (MEDIA) {
+				const float4 q1 = ldg4(pp + 1);
+				if (type == PRIM_MEDIUM_SPHERE) {
+					uint32_t mi = __float_as_uint(q1.y);
+					float u = rt::rng4(mr.seed, mr.pixel, mr.sample, mr.bounce, rt::STREAM_MEDIUM0 + mi).x;
+					t = medium_sphere_hit(o, d, a, q0, q1.x, u, tbest);
+				} else {
+					const float4 q2 = ldg4(pp + 2), q3 = ldg4(pp + 3);
+					uint32_t mi = __float_as_uint(q3.x);
+					float u = rt::rng4(mr.seed, mr.pixel, mr.sample, mr.bounce, rt::STREAM_MEDIUM0 + mi).x;
+					t = medium_box_hit(o, d, a, q0, q1, q2, u, tbest);
+				}
+			}
+			if (t < tbest) { tbest = t; best = code; }   // "if (t >= rec.distance) return false"  SphereHittable.cu:58
+		}
+		if (sp == 0) break;
+		--sp; cur = stack[sp * TRAVERSE_THREADS];
+	}
+	tbest_out = tbest; code_out = best;
+}
+
+template <bool MEDIA>
+__global__ void __launch_bounds__(TRAVERSE_THREADS)
+traverse_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
+	__shared__ int s_stack[STACK_SIZE * TRAVERSE_THREADS];
+	const uint32_t n = wv.n_live[bounce];
+	if (n == 0) return;
+	const uint32_t batch = *wv.batch_index;
+	const int lane = threadIdx.x & 31;
+	const float4* __restrict__ ro = wv.ray_o[bounce & 1];
+	const float4* __restrict__ rd = wv.ray_d[bounce & 1];
+	uint32_t* counter = wv.work + 2 * bounce;
+	for (;;) {
+		uint32_t base = 0;
+		if (lane == 0) base = atomicAdd(counter, 32u);
+		base = __shfl_sync(FULL_MASK, base, 0);
+		if (base >= n) break;
+		uint32_t i = base + lane;
+		if (i < n) {
+			float4 fo = ro[i], fd = rd[i];
+			MediumRng mr{0, 0, 0, 0};
+			if (MEDIA) {
+				mr.seed = bp.seed; mr.bounce = bounce;
+				path_pixel_sample(bp, batch, __float_as_uint(fd.w), mr.pixel, mr.sample);
+			}
+			float t; int code;
+			trace_ray<MEDIA>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code);
+			wv.hit[i] = make_int2(__float_as_int(t), code);
+		}
+		__syncwarp();
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// surface reconstruction + textures + materials
+
+struct Surface { v3 p, n_shade, n_geom; float u, v; };
+
+// What Sphere::getNormal / MovingSphere::getNormal hand to materials: the outward normal
+// (p - c) / r, never flipped (SphereHittable.cu:43-50,64,100).  Quads face the ray (book).
+__device__ __forceinline__ void reconstruct(const SceneView& sv, int code, v3 o, v3 d, float time, float t, bool want_uv, Surface& s) {
+	const int type = code & 7;
+	const float4* pp = sv.prims + 4 * (size_t)(code >> 3);
+	const float4 q0 = ldg4(pp);
+	s.p = rt::madd(d, t, o);
+	s.u = 0.0f; s.v = 0.0f;
+	if (type == PRIM_SPHERE || type == PRIM_MOVING_SPHERE) {
+		v3 c = xyz(q0);
+		if (type == PRIM_MOVING_SPHERE) c = rt::mix(c, xyz(ldg4(pp + 1)), time);
+		s.n_geom = rt::divs(rt::sub(s.p, c), q0.w);
+		s.n_shade = s.n_geom;
+		if (want_uv) {   // book sphere::get_sphere_uv, on the normal taken back to the sphere's own frame
+			const float4 qr = ldg4(pp + (type == PRIM_MOVING_SPHERE ? 2 : 1));
+			const float nx = fmaf(qr.x, s.n_geom.x, -(qr.y * s.n_geom.z)), nz = fmaf(qr.y, s.n_geom.x, qr.x * s.n_geom.z);
+			float theta = acosf(-s.n_geom.y);
+			float phi = atan2f(-nz, nx) + 3.14159265358979323846f;
+			s.u = phi / 6.28318530717958647692f;
+			s.v = theta / 3.14159265358979323846f;
+		}
+	} else if (type == PRIM_QUAD || type == PRIM_TRIANGLE) {
+		const float4 q1 = ldg4(pp + 1), q2 = ldg4(pp + 2), q3 = ldg4(pp + 3);
+		v3 N = rt::mk(q1.w, q2.w, q3.w);
+		s.n_geom = N;
+		s.n_shade = rt::dot(d, N) > 0.0f ? rt::neg(N) : N;
+		if (want_uv) {
+			v3 planar = rt::sub(s.p, xyz(q0));
+			s.u = rt::dot(xyz(q3), rt::cross(planar, xyz(q2)));
+			s.v = rt::dot(xyz(q3), rt::cross(xyz(q1), planar));
+		}
+	} else {  // medium: normal arbitrary (book constant_medium::hit)
+		s.n_geom = rt::mk(1.0f, 0.0f, 0.0f);
+		s.n_shade = s.n_geom;
+	}
+}
+
+__device__ __forceinline__ float sin_any(float x) {
+	float r = x * 0.15915494309189535f;
+	r = r - floorf(r);
+	float s, c; rt::sincos2pi(r, s, c);
+	return s;
+}
+
+// Book perlin::noise with Hermite-smoothed trilinear interpolation of gradient dot products.
+__device__ float perlin_noise(const float* __restrict__ grad, const int* __restrict__ perm, v3 p) {
+	float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+	float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+	int i = (int)fx, j = (int)fy, k = (int)fz;
+	float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+	float accum = 0.0f;
+#pragma unroll
+	for (int di = 0; di < 2; ++di)
+#pragma unroll
+		for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+			for (int dk = 0; dk < 2; ++dk) {
+				int g = perm[(i + di) & 255] ^ perm[256 + ((j + dj) & 255)] ^ perm[512 + ((k + dk) & 255)];
+				v3 c = rt::mk(grad[3 * g], grad[3 * g + 1], grad[3 * g + 2]);
+				v3 wv = rt::mk(u - (float)di, v - (float)dj, w - (float)dk);
+				float wi = di ? uu : 1.0f - uu, wj = dj ? vv : 1.0f - vv, wk = dk ? ww : 1.0f - ww;
+				accum = fmaf(wi * wj * wk, rt::dot(c, wv), accum);
+			}
+	return accum;
+}
+
+__device__ v3 texture_value(const SceneView& sv, int tex, float u, float v, v3 p) {
+	for (int guard = 0; guard < 16; ++guard) {
+		const float4 t0 = ldg4(sv.textures + 3 * tex);
+		const int kind = __float_as_int(t0.x);
+		if (kind == RTB_TEX_SOLID) { return xyz(ldg4(sv.textures + 3 * tex + 1)); }
+		if (kind == RTB_TEX_CHECKER) {
+			// checker_texture::value  cu_Textures.cuh:32-39: C cast (truncation) and C '%'
+			float inv = t0.w;
+			int sum = (int)(p.x * inv) + (int)(p.y * inv) + (int)(p.z * inv);
+			tex = (sum % 2 == 0) ? __float_as_int(t0.y) : __float_as_int(t0.z);
+			continue;
+		}
+		const float4 t2 = ldg4(sv.textures + 3 * tex + 2);
+		const int w = __float_as_int(t2.x), h = __float_as_int(t2.y);
+		const uint32_t off = __float_as_uint(t2.z);
+		if (kind == RTB_TEX_IMAGE) {   // book image_texture::value (nearest texel, bytes / 255)
+			float uc = fminf(fmaxf(u, 0.0f), 1.0f), vc = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
+			int i = (int)(uc * (float)w), j = (int)(vc * (float)h);
+			i = i < w - 1 ? i : w - 1; j = j < h - 1 ? j : h - 1;
+			const uint8_t* px = sv.blob + off + 3 * ((size_t)j * w + i);
+			const float sc = 1.0f / 255.0f;
+			return rt::mk(sc * (float)px[0], sc * (float)px[1], sc * (float)px[2]);
+		}
+		// RTB_TEX_NOISE: book noise_texture::value = 0.5 * (1 + sin(scale * p.z + 10 * turb(p, 7)))
+		const float* grad = reinterpret_cast<const float*>(sv.blob + off);
+		const int* perm = reinterpret_cast<const int*>(sv.blob + off + 256 * 3 * 4);
+		float accum = 0.0f, weight = 1.0f; v3 tp = p;
+		for (int k = 0; k < 7; ++k) {
+			accum = fmaf(weight, perlin_noise(grad, perm, tp), accum);
+			weight *= 0.5f; tp = rt::mul(tp, 2.0f);
+		}
+		float turb = fabsf(accum);
+		float val = 0.5f * (1.0f + sin_any(fmaf(t0.w, p.z, 10.0f * turb)));
+		return rt::mk(val, val, val);
+	}
+	return rt::mk(0.0f, 0.0f, 0.0f);
+}
+
+__device__ __forceinline__ bool texture_needs_uv(const SceneView& sv, int tex) {
+	if (tex < 0) return false;
+	const int kind = __float_as_int(ldg4(sv.textures + 3 * tex).x);
+	return kind != RTB_TEX_SOLID && kind != RTB_TEX_NOISE;   // checker children may be images
+}
+
+// Material::Scatter for every material kind.  Returns 0 = absorbed (path ends black),
+// 1 = scattered (dir/attenuation valid), 2 = emitted (attenuation holds the emitted radiance).
+__device__ __forceinline__ int scatter(const SceneView& sv, int mat, const Surface& s, v3 d, const rt::f4& r, v3& dir, v3& att) {
+	const float4 m0 = ldg4(sv.materials + 2 * mat), m1 = ldg4(sv.materials + 2 * mat + 1);
+	const int kind = __float_as_int(m0.x), tex = __float_as_int(m0.y);
+	const float param = m0.z;
+	v3 albedo = tex >= 0 ? texture_value(sv, tex, s.u, s.v, s.p) : xyz(m1);
+	switch (kind) {
+	case RTB_MAT_LAMBERTIAN: {   // LambertianAbstract / LambertianTexture  cu_materials.cuh:26-40,52-64
+		dir = rt::add(s.n_shade, rt::unit_sphere(r.x, r.y));
+		if (rt::near_zero(dir, 1e-9f)) return 0;
+		att = albedo; return 1;
+	}
+	case RTB_MAT_METAL: {        // MetalAbstract  cu_materials.cuh:77-95 (in_ray.d is not normalised)
+		dir = rt::madd(rt::unit_sphere(r.x, r.y), param, rt::reflect(d, s.n_shade));
+		if (rt::dot(dir, s.n_shade) < 0.0f || rt::near_zero(dir, 1e-9f)) return 0;
+		att = albedo; return 1;
+	}
+	case RTB_MAT_DIELECTRIC: {   // DielectricAbstract  cu_materials.cuh:115-143, reflectance :99-104
+		v3 n = s.n_geom;
+		bool back = rt::dot(d, n) > 0.0f;          // isBackfacing  ray_data.cuh:44-46
+		if (back) n = rt::neg(n);
+		float ratio = back ? param : 1.0f / param;
+		v3 ud = rt::normalize(d);
+		float cos_theta = fminf(rt::dot(rt::neg(ud), n), 1.0f);
+		float sin_theta = sqrtf(fmaf(-cos_theta, cos_theta, 1.0f));
+		float r0 = (1.0f - ratio) / (1.0f + ratio); r0 = r0 * r0;
+		float x = 1.0f - cos_theta, x2 = x * x;
+		float prob = fmaf(1.0f - r0, x2 * x2 * x, r0);   // powf(1 - cos, 5) as exact products
+		if (ratio * sin_theta > 1.0f || prob > r.z) {
+			dir = rt::reflect(ud, n);
+		} else {                                   // glm::refract  func_geometric.inl:113-124
+			float dv = rt::dot(n, ud);
+			float k = fmaf(-(ratio * ratio), fmaf(-dv, dv, 1.0f), 1.0f);
+			if (k < 0.0f) return 0;
+			float coef = fmaf(ratio, dv, sqrtf(k));
+			dir = rt::mk(fmaf(-coef, n.x, ratio * ud.x), fmaf(-coef, n.y, ratio * ud.y), fmaf(-coef, n.z, ratio * ud.z));
+		}
+		if (dir.x == 0.0f && dir.y == 0.0f && dir.z == 0.0f) return 0;
+		att = albedo; return 1;
+	}
+	case RTB_MAT_ISOTROPIC: {    // book isotropic::scatter
+		dir = rt::unit_sphere(r.x, r.y);
+		att = albedo; return 1;
+	}
+	default:                     // RTB_MAT_DIFFUSE_LIGHT: emits, never scatters (book diffuse_light)
+		att = albedo; return 2;
+	}
+}
+
+__device__ __forceinline__ v3 background(const SceneView& sv, v3 d) {
+	if (sv.background_mode == RTB_BG_CONSTANT) return rt::mk(sv.bg_r, sv.bg_g, sv.bg_b);
+	// Renderer.cu:149-151: t = normalize(d).y * 0.5 + 0.5; lerp((0.1,0.2,0.4), (0.9,0.9,0.99), t)
+	float ny = d.y * (1.0f / sqrtf(rt::dot(d, d)));
+	float t = fmaf(ny, 0.5f, 0.5f);
+	return rt::mk(fmaf(0.9f - 0.1f, t, 0.1f), fmaf(0.9f - 0.2f, t, 0.2f), fmaf(0.99f - 0.4f, t, 0.4f));
+}
+
+// ------------------------------------------------------------------------------------------------
+// shade: one path segment of sample_world (Renderer.cu:146-176) + block-level queue compaction
+
+__global__ void __launch_bounds__(SHADE_THREADS)
+shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
+	__shared__ uint32_t s_chunk, s_base;
+	__shared__ uint32_t s_warp[SHADE_THREADS / 32];
+	const uint32_t n = wv.n_live[bounce];
+	if (n == 0) return;
+	const uint32_t batch = *wv.batch_index;
+	const int in = bounce & 1, out = in ^ 1;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const bool last = bounce + 1 >= bp.max_depth;
+	uint32_t* counter = wv.work + 2 * bounce + 1;
+	for (;;) {
+		if (threadIdx.x == 0) s_chunk = atomicAdd(counter, (uint32_t)SHADE_THREADS);
+		__syncthreads();
+		const uint32_t base = s_chunk;
+		if (base >= n) break;
+		const uint32_t i = base + threadIdx.x;
+		bool alive = false;
+		float4 no = make_float4(0, 0, 0, 0), nd = no, nt = no;
+		if (i < n) {
+			const float4 fo = wv.ray_o[in][i], fd = wv.ray_d[in][i], ft = wv.thr[in][i];
+			const int2 h = wv.hit[i];
+			const uint32_t path = __float_as_uint(fd.w);
+			const v3 o = xyz(fo), d = xyz(fd), thr = xyz(ft);
+			if (h.y < 0) {
+				v3 c = rt::mulv(thr, background(sv, d));          // miss: throughput * sky   Renderer.cu:153
+				wv.contrib[path] = make_float4(c.x, c.y, c.z, 0.0f);
+			} else {
+				const float t = __int_as_float(h.x);
+				const int2 info = __ldg(sv.prim_info + (h.y >> 3));
+				const int tex = __float_as_int(ldg4(sv.materials + 2 * info.x).y);
+				Surface s;
+				reconstruct(sv, h.y, o, d, fo.w, t, texture_needs_uv(sv, tex), s);
+				uint32_t pixel, sample;
+				path_pixel_sample(bp, batch, path, pixel, sample);
+				const rt::f4 r = rt::rng4(bp.seed, pixel, sample, bounce, rt::STREAM_SCATTER);
+				v3 dir, att;
+				const int res = scatter(sv, info.x, s, d, r, dir, att);
+				if (res == 2) {
+					v3 c = rt::mulv(thr, att);
+					wv.contrib[path] = make_float4(c.x, c.y, c.z, 0.0f);
+				} else if (res == 1 && !last) {
+					// scatter_ray = Ray(at(t), dir, time); o += d * 0.001   Renderer.cu:168-175
+					v3 o2 = rt::madd(dir, 0.001f, s.p);
+					v3 t2 = rt::mulv(thr, att);
+					no = make_float4(o2.x, o2.y, o2.z, fo.w);
+					nd = make_float4(dir.x, dir.y, dir.z, fd.w);
+					nt = make_float4(t2.x, t2.y, t2.z, 0.0f);
+					alive = true;
+				}
+			}
+		}
+		// live-path compaction: warp ballot/popc, one global atomic per block
+		const uint32_t mask = __ballot_sync(FULL_MASK, alive);
+		if (lane == 0) s_warp[warp] = __popc(mask);
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			uint32_t tot = 0;
+#pragma unroll
+			for (int w = 0; w < SHADE_THREADS / 32; ++w) { uint32_t c = s_warp[w]; s_warp[w] = tot; tot += c; }
+			s_base = tot ? atomicAdd(wv.n_live + bounce + 1, tot) : 0u;
+		}
+		__syncthreads();
+		if (alive) {
+			const uint32_t pos = s_base + s_warp[warp] + __popc(mask & ((1u << lane) - 1u));
+			wv.ray_o[out][pos] = no; wv.ray_d[out][pos] = nd; wv.thr[out][pos] = nt;
+		}
+		__syncthreads();
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// accumulate + batch epilogue + resolve
+
+__global__ void __launch_bounds__(STREAM_THREADS)
+accumulate_kernel(BatchParams bp, WaveView wv, float4* __restrict__ accum, float4* __restrict__ accum2) {
+	const uint32_t batch = *wv.batch_index;
+	const uint32_t ns = batch_sample_count(bp, batch);
+	if (ns == 0) return;
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for (uint32_t pl = blockIdx.x * blockDim.x + threadIdx.x; pl < bp.npix; pl += stride) {
+		float sx = 0.0f, sy = 0.0f, sz = 0.0f, qx = 0.0f, qy = 0.0f, qz = 0.0f;
+		for (uint32_t s = 0; s < ns; ++s) {   // fixed sample order: deterministic sums
+			const float4 c = wv.contrib[(size_t)s * bp.npix + pl];
+			sx += c.x; sy += c.y; sz += c.z;
+			if (bp.variance) { qx = fmaf(c.x, c.x, qx); qy = fmaf(c.y, c.y, qy); qz = fmaf(c.z, c.z, qz); }
+		}
+		const uint32_t gid = bp.row_begin * bp.width + pl;
+		float4 a = accum[gid];
+		a.x += sx; a.y += sy; a.z += sz; a.w += (float)ns;
+		accum[gid] = a;
+		if (bp.variance) {
+			float4 q = accum2[gid];
+			q.x += qx; q.y += qy; q.z += qz; q.w += (float)ns;
+			accum2[gid] = q;
+		}
+	}
+}
+
+__global__ void end_batch_kernel(BatchParams bp, WaveView wv) {
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	unsigned long long rays = 0;
+	for (uint32_t b = 0; b < bp.max_depth; ++b) rays += wv.n_live[b];
+	wv.totals[0] += wv.n_live[0];
+	wv.totals[1] += rays;
+	*wv.batch_index += 1;
+}
+
+__global__ void __launch_bounds__(STREAM_THREADS)
+resolve_kernel(const float4* __restrict__ accum, float4* __restrict__ out, uint32_t n) {
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const float4 a = accum[i];
+		const float inv = 1.0f / a.w;                              // radiance *= 1.0f / spp   Renderer.cu:206
+		float r = a.x * inv, g = a.y * inv, b = a.z * inv;
+		r = fminf(fmaxf(r, 0.0f), 1.0f); g = fminf(fmaxf(g, 0.0f), 1.0f); b = fminf(fmaxf(b, 0.0f), 1.0f);
+		out[i] = make_float4(sqrtf(r), sqrtf(g), sqrtf(b), 1.0f);  // clamp, gamma 2, alpha 1   :209-214
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// hit-record parity hook
+
+__global__ void __launch_bounds__(TRAVERSE_THREADS)
+trace_rays_kernel(SceneView sv, const float4* __restrict__ ro, const float4* __restrict__ rd, uint32_t n,
+                  int2* __restrict__ hit, uint32_t* counter) {
+	__shared__ int s_stack[STACK_SIZE * TRAVERSE_THREADS];
+	const int lane = threadIdx.x & 31;
+	for (;;) {
+		uint32_t base = 0;
+		if (lane == 0) base = atomicAdd(counter, 32u);
+		base = __shfl_sync(FULL_MASK, base, 0);
+		if (base >= n) break;
+		uint32_t i = base + lane;
+		if (i < n) {
+			float4 fo = ro[i], fd = rd[i];
+			MediumRng mr{0, 0, 0, 0};
+			float t; int code;
+			trace_ray<false>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code);
+			hit[i] = make_int2(__float_as_int(t), code);
+		}
+		__syncwarp();
+	}
+}
+
+__global__ void __launch_bounds__(STREAM_THREADS)
+hit_record_kernel(SceneView sv, const float4* __restrict__ ro, const float4* __restrict__ rd, const int2* __restrict__ hit,
+                  uint32_t n, rtb_hit* __restrict__ out) {
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		rtb_hit r;
+		const int2 h = hit[i];
+		r.t = __int_as_float(h.x);
+		r.pad[0] = r.pad[1] = r.pad[2] = 0;
+		if (h.y < 0) {
+			r.t = FLT_MAX; r.prim = -1; r.object = -1; r.material = -1; r.front_face = 0; r.u = r.v = 0.0f;
+			r.p[0] = r.p[1] = r.p[2] = 0.0f; r.n[0] = r.n[1] = r.n[2] = 0.0f;
+		} else {
+			const float4 fo = ro[i], fd = rd[i];
+			const int2 info = __ldg(sv.prim_info + (h.y >> 3));
+			Surface s;
+			reconstruct(sv, h.y, xyz(fo), xyz(fd), fo.w, r.t, true, s);
+			r.prim = h.y >> 3; r.object = info.y; r.material = info.x;
+			r.p[0] = s.p.x; r.p[1] = s.p.y; r.p[2] = s.p.z;
+			r.n[0] = s.n_shade.x; r.n[1] = s.n_shade.y; r.n[2] = s.n_shade.z;
+			r.front_face = rt::dot(xyz(fd), s.n_geom) > 0.0f ? 0 : 1;
+			r.u = s.u; r.v = s.v;
+		}
+		out[i] = r;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launch wrappers
+
+void query_occupancy(int device, LaunchCfg& lc) {
+	cudaDeviceProp prop{};
+	cudaGetDeviceProperties(&prop, device);
+	int sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+	int occ_t = 0, occ_tm = 0, occ_s = 0, occ_g = 0;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, traverse_kernel<false>, TRAVERSE_THREADS, 0);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tm, traverse_kernel<true>, TRAVERSE_THREADS, 0);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, shade_kernel, SHADE_THREADS, 0);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, generate_kernel, STREAM_THREADS, 0);
+	int occ_trav = occ_t < occ_tm ? occ_t : occ_tm;
+	lc.blocks_traverse = sms * (occ_trav > 0 ? occ_trav : 1);
+	lc.blocks_shade = sms * (occ_s > 0 ? occ_s : 1);
+	lc.blocks_stream = sms * (occ_g > 0 ? occ_g : 1);
+}
+
+void launch_generate(const BatchParams& bp, const rtb_camera& cam, const WaveView& wv, const LaunchCfg& lc, cudaStream_t st) {
+	generate_kernel<<<lc.blocks_stream, STREAM_THREADS, 0, st>>>(bp, cam, wv);
+}
+void launch_traverse(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st) {
+	// media need the per-path RNG inside traversal; scenes without media skip that code entirely
+	if (sv.has_media) traverse_kernel<true><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce);
+	else traverse_kernel<false><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce);
+}
+void launch_shade(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st) {
+	shade_kernel<<<lc.blocks_shade, SHADE_THREADS, 0, st>>>(sv, bp, wv, bounce);
+}
+void launch_accumulate(const BatchParams& bp, const WaveView& wv, float4* accum, float4* accum2, const LaunchCfg& lc, cudaStream_t st) {
+	accumulate_kernel<<<lc.blocks_stream, STREAM_THREADS, 0, st>>>(bp, wv, accum, accum2);
+	end_batch_kernel<<<1, 32, 0, st>>>(bp, wv);
+}
+void launch_resolve(const float4* accum, float4* out, uint32_t n, cudaStream_t st) {
+	int blocks = (int)((n + STREAM_THREADS - 1) / STREAM_THREADS); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+	resolve_kernel<<<blocks, STREAM_THREADS, 0, st>>>(accum, out, n);
+}
+void launch_trace_rays(const SceneView& sv, const float4* ray_o, const float4* ray_d, uint32_t n, int2* hit_tmp,
+                       rtb_hit* hits_out, uint32_t* work_counter, const LaunchCfg& lc, cudaStream_t st) {
+	cudaMemsetAsync(work_counter, 0, sizeof(uint32_t), st);
+	trace_rays_kernel<<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, ray_o, ray_d, n, hit_tmp, work_counter);
+	hit_record_kernel<<<lc.blocks_stream, STREAM_THREADS, 0, st>>>(sv, ray_o, ray_d, hit_tmp, n, hits_out);
+}
+
+}  // namespace rtb

@@ -1,0 +1,67 @@
+// rtb_kernels.h — launch interface of the wavefront kernels (rtb_kernels.cu).
+#ifndef RTB_KERNELS_H
+#define RTB_KERNELS_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rtb.h"
+
+namespace rtb {
+
+// Device views of the flattened scene (all pointers 64-byte aligned).
+struct SceneView {
+	const float4* nodes;        // 4 x float4 per inner node
+	const float4* prims;        // 4 x float4 per primitive
+	const int2* prim_info;      // (material, object)
+	const float4* materials;    // 2 x float4 per material
+	const float4* textures;     // 3 x float4 per texture
+	const uint8_t* blob;        // image texels / Perlin tables
+	int32_t root_ref;
+	int32_t n_prims;
+	int32_t has_media;          // selects the traverse variant that draws free-flight distances
+	int32_t background_mode;
+	float bg_r, bg_g, bg_b;
+};
+
+// One batch = `samples_per_batch` consecutive samples of every pixel of the row range.
+struct BatchParams {
+	uint32_t width, height;
+	uint32_t row_begin, n_rows;
+	uint32_t npix;              // width * n_rows
+	uint32_t sample_begin, sample_end;
+	uint32_t samples_per_batch;
+	uint32_t max_depth;
+	uint32_t seed;
+	uint32_t variance;
+};
+
+// Wavefront queues, structure-of-arrays, double buffered by bounce parity.
+struct WaveView {
+	float4* ray_o[2];           // (o.xyz, time)
+	float4* ray_d[2];           // (d.xyz, path id bits)
+	float4* thr[2];             // (throughput rgb, -)
+	int2* hit;                  // (t bits, leaf code or -1)
+	float4* contrib;            // per path: radiance carried by the terminated path
+	uint32_t* n_live;           // [max_depth + 1] queue lengths per bounce
+	uint32_t* work;             // [2 * (max_depth + 1)] dynamic work counters (traverse, shade)
+	uint32_t* batch_index;      // device-side batch counter (graph replays need no new arguments)
+	unsigned long long* totals; // [0] paths, [1] rays
+};
+
+struct LaunchCfg { int blocks_traverse, blocks_shade, blocks_stream; };
+
+void launch_generate(const BatchParams& bp, const rtb_camera& cam, const WaveView& wv, const LaunchCfg& lc, cudaStream_t st);
+void launch_traverse(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st);
+void launch_shade(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st);
+void launch_accumulate(const BatchParams& bp, const WaveView& wv, float4* accum, float4* accum2, const LaunchCfg& lc, cudaStream_t st);
+void launch_resolve(const float4* accum, float4* out, uint32_t n, cudaStream_t st);
+
+// Parity hook: closest hits + full hit records for explicit rays (media skipped).
+void launch_trace_rays(const SceneView& sv, const float4* ray_o, const float4* ray_d, uint32_t n, int2* hit_tmp,
+                       rtb_hit* hits_out, uint32_t* work_counter, const LaunchCfg& lc, cudaStream_t st);
+
+void query_occupancy(int device, LaunchCfg& lc);
+
+}  // namespace rtb
+#endif

@@ -1,0 +1,386 @@
+// rtb_render.cu — renderer object behind the C ABI: device memory, batch scheduling, CUDA-graph
+// replay of the per-batch wavefront sequence, download and the parity hooks.
+//
+// Replaces Renderer::MakeRenderer / Render / DownloadRenderbuffer (main/src/Renderer.cu:31-137) and the
+// scene upload of BVH_Handle's ctor (main/src/rt_engine/geometry/BVH.cu:110-120): one arena of aligned
+// SoA buffers instead of ~3 device allocations + a <<<1,1>>> constructor launch per object.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rtb_kernels.h"
+#include "rtb_scene.h"
+
+using namespace rtb;
+
+#define CUDA_TRY(expr)                                                                                  \
+	do {                                                                                                \
+		cudaError_t _e = (expr);                                                                        \
+		if (_e != cudaSuccess)                                                                          \
+			return fail(RTB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                 \
+	} while (0)
+
+struct rtb_renderer {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+	bool timed = false;
+
+	// scene arena
+	void* d_scene = nullptr; size_t scene_bytes = 0;
+	SceneView sv{};
+	bool has_scene = false;
+	uint64_t scene_version = 0;
+	rtb_camera cam{};
+	bool has_cam = false;
+
+	// framebuffers
+	uint32_t width = 0, height = 0;
+	float4 *d_accum = nullptr, *d_accum2 = nullptr, *d_out = nullptr;
+
+	// wavefront queues
+	void* d_wave = nullptr; size_t wave_paths = 0; uint32_t wave_depth = 0;
+	WaveView wv{};
+	LaunchCfg lc{};
+
+	// cached per-batch graph
+	cudaGraphExec_t graph_exec = nullptr;
+	BatchParams graph_bp{}; rtb_camera graph_cam{}; uint64_t graph_scene_version = 0; bool graph_valid = false;
+	float4 *graph_accum = nullptr;
+
+	uint64_t launches = 0, batches = 0;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static void free_graph(rtb_renderer* r) {
+	if (r->graph_exec) { cudaGraphExecDestroy(r->graph_exec); r->graph_exec = nullptr; }
+	r->graph_valid = false;
+}
+
+extern "C" {
+
+int rtb_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+int rtb_renderer_create(rtb_renderer** out, int device) {
+	if (!out) return fail(RTB_ERR_INVALID, "rtb_renderer_create: null out");
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) {
+		cudaGetLastError();
+		return fail(RTB_ERR_CUDA, std::string("rtb_renderer_create: no usable CUDA device (") + cudaGetErrorString(e) +
+		                              "); this library has no CPU fallback");
+	}
+	if (device < 0 || device >= n) return fail(RTB_ERR_INVALID, "rtb_renderer_create: bad device index");
+	CUDA_TRY(cudaSetDevice(device));
+	rtb_renderer* r = new rtb_renderer();
+	r->device = device;
+	CUDA_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+	CUDA_TRY(cudaEventCreateWithFlags(&r->ev_in, cudaEventDisableTiming));
+	CUDA_TRY(cudaEventCreateWithFlags(&r->ev_out, cudaEventDisableTiming));
+	CUDA_TRY(cudaEventCreate(&r->ev_t0));
+	CUDA_TRY(cudaEventCreate(&r->ev_t1));
+	query_occupancy(device, r->lc);
+	*out = r;
+	return RTB_OK;
+}
+
+void rtb_renderer_destroy(rtb_renderer* r) {
+	if (!r) return;
+	cudaSetDevice(r->device);
+	cudaStreamSynchronize(r->stream);
+	free_graph(r);
+	cudaFree(r->d_scene); cudaFree(r->d_accum); cudaFree(r->d_accum2); cudaFree(r->d_out); cudaFree(r->d_wave);
+	cudaEventDestroy(r->ev_in); cudaEventDestroy(r->ev_out); cudaEventDestroy(r->ev_t0); cudaEventDestroy(r->ev_t1);
+	cudaStreamDestroy(r->stream);
+	delete r;
+}
+
+int rtb_renderer_set_scene(rtb_renderer* r, rtb_scene* s) {
+	if (!r || !s) return fail(RTB_ERR_INVALID, "rtb_renderer_set_scene: null argument");
+	FlatScene fs;
+	int rc = flatten(*s, fs);
+	if (rc) return rc;
+	CUDA_TRY(cudaSetDevice(r->device));
+	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	// one arena, every section 256-byte aligned
+	size_t off_nodes = 0;
+	size_t off_prims = align_up(off_nodes + fs.nodes.size() * sizeof(DevNode), 256);
+	size_t off_info = align_up(off_prims + fs.prims.size() * sizeof(DevPrim), 256);
+	size_t off_mats = align_up(off_info + fs.prim_info.size() * sizeof(DevPrimInfo), 256);
+	size_t off_texs = align_up(off_mats + fs.materials.size() * sizeof(DevMaterial), 256);
+	size_t off_blob = align_up(off_texs + fs.textures.size() * sizeof(DevTexture), 256);
+	size_t total = align_up(off_blob + fs.blob.size(), 256) + 256;
+	std::vector<uint8_t> staging(total, 0);
+	if (!fs.nodes.empty()) memcpy(staging.data() + off_nodes, fs.nodes.data(), fs.nodes.size() * sizeof(DevNode));
+	memcpy(staging.data() + off_prims, fs.prims.data(), fs.prims.size() * sizeof(DevPrim));
+	memcpy(staging.data() + off_info, fs.prim_info.data(), fs.prim_info.size() * sizeof(DevPrimInfo));
+	if (!fs.materials.empty()) memcpy(staging.data() + off_mats, fs.materials.data(), fs.materials.size() * sizeof(DevMaterial));
+	if (!fs.textures.empty()) memcpy(staging.data() + off_texs, fs.textures.data(), fs.textures.size() * sizeof(DevTexture));
+	if (!fs.blob.empty()) memcpy(staging.data() + off_blob, fs.blob.data(), fs.blob.size());
+	if (total > r->scene_bytes) {
+		cudaFree(r->d_scene); r->d_scene = nullptr; r->scene_bytes = 0;
+		CUDA_TRY(cudaMalloc(&r->d_scene, total));
+		r->scene_bytes = total;
+	}
+	CUDA_TRY(cudaMemcpy(r->d_scene, staging.data(), total, cudaMemcpyHostToDevice));
+	uint8_t* base = static_cast<uint8_t*>(r->d_scene);
+	r->sv.nodes = reinterpret_cast<const float4*>(base + off_nodes);
+	r->sv.prims = reinterpret_cast<const float4*>(base + off_prims);
+	r->sv.prim_info = reinterpret_cast<const int2*>(base + off_info);
+	r->sv.materials = reinterpret_cast<const float4*>(base + off_mats);
+	r->sv.textures = reinterpret_cast<const float4*>(base + off_texs);
+	r->sv.blob = base + off_blob;
+	r->sv.root_ref = fs.root_ref;
+	r->sv.n_prims = (int32_t)fs.prims.size();
+	r->sv.has_media = fs.n_media > 0;
+	r->sv.background_mode = fs.background_mode;
+	r->sv.bg_r = fs.background[0]; r->sv.bg_g = fs.background[1]; r->sv.bg_b = fs.background[2];
+	r->has_scene = true;
+	r->scene_version++;
+	return RTB_OK;
+}
+
+int rtb_renderer_set_camera(rtb_renderer* r, const rtb_camera* cam) {
+	if (!r || !cam) return fail(RTB_ERR_INVALID, "rtb_renderer_set_camera: null argument");
+	if (cam->kind < RTB_CAM_PINHOLE || cam->kind > RTB_CAM_MOTION) return fail(RTB_ERR_INVALID, "rtb_renderer_set_camera: bad kind");
+	r->cam = *cam; r->has_cam = true;
+	return RTB_OK;
+}
+
+static int ensure_framebuffer(rtb_renderer* r, uint32_t w, uint32_t h) {
+	if (r->width == w && r->height == h && r->d_accum) return RTB_OK;
+	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	cudaFree(r->d_accum); cudaFree(r->d_accum2); cudaFree(r->d_out);
+	r->d_accum = r->d_accum2 = r->d_out = nullptr;
+	size_t bytes = (size_t)w * h * sizeof(float4);
+	CUDA_TRY(cudaMalloc(&r->d_accum, bytes));
+	CUDA_TRY(cudaMalloc(&r->d_accum2, bytes));
+	CUDA_TRY(cudaMalloc(&r->d_out, bytes));
+	CUDA_TRY(cudaMemset(r->d_accum, 0, bytes));
+	CUDA_TRY(cudaMemset(r->d_accum2, 0, bytes));
+	CUDA_TRY(cudaMemset(r->d_out, 0, bytes));
+	r->width = w; r->height = h;
+	free_graph(r);
+	return RTB_OK;
+}
+
+static int ensure_wave(rtb_renderer* r, size_t paths, uint32_t depth) {
+	if (paths <= r->wave_paths && depth <= r->wave_depth && r->d_wave) return RTB_OK;
+	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	free_graph(r);
+	cudaFree(r->d_wave); r->d_wave = nullptr;
+	size_t P = align_up(paths, 256);
+	size_t off = 0;
+	auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+	size_t o_ro0 = take(P * 16), o_ro1 = take(P * 16), o_rd0 = take(P * 16), o_rd1 = take(P * 16);
+	size_t o_t0 = take(P * 16), o_t1 = take(P * 16), o_hit = take(P * 8), o_con = take(P * 16);
+	size_t o_live = take((depth + 2) * 4), o_work = take(2 * (depth + 2) * 4), o_batch = take(256), o_tot = take(256);
+	CUDA_TRY(cudaMalloc(&r->d_wave, off));
+	CUDA_TRY(cudaMemset(r->d_wave, 0, off));
+	uint8_t* b = static_cast<uint8_t*>(r->d_wave);
+	r->wv.ray_o[0] = (float4*)(b + o_ro0); r->wv.ray_o[1] = (float4*)(b + o_ro1);
+	r->wv.ray_d[0] = (float4*)(b + o_rd0); r->wv.ray_d[1] = (float4*)(b + o_rd1);
+	r->wv.thr[0] = (float4*)(b + o_t0); r->wv.thr[1] = (float4*)(b + o_t1);
+	r->wv.hit = (int2*)(b + o_hit); r->wv.contrib = (float4*)(b + o_con);
+	r->wv.n_live = (uint32_t*)(b + o_live); r->wv.work = (uint32_t*)(b + o_work);
+	r->wv.batch_index = (uint32_t*)(b + o_batch); r->wv.totals = (unsigned long long*)(b + o_tot);
+	r->wave_paths = P; r->wave_depth = depth;
+	return RTB_OK;
+}
+
+static void enqueue_batch(rtb_renderer* r, const BatchParams& bp, cudaStream_t st) {
+	launch_generate(bp, r->cam, r->wv, r->lc, st);
+	for (uint32_t b = 0; b < bp.max_depth; ++b) {
+		launch_traverse(r->sv, bp, r->wv, b, r->lc, st);
+		launch_shade(r->sv, bp, r->wv, b, r->lc, st);
+	}
+	launch_accumulate(bp, r->wv, r->d_accum, r->d_accum2, r->lc, st);
+}
+
+int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
+	if (!r || !p) return fail(RTB_ERR_INVALID, "rtb_render: null argument");
+	if (!r->has_scene) return fail(RTB_ERR_STATE, "rtb_render: no scene (rtb_renderer_set_scene)");
+	if (!r->has_cam) return fail(RTB_ERR_STATE, "rtb_render: no camera (rtb_renderer_set_camera)");
+	if (p->width == 0 || p->height == 0 || p->max_depth == 0) return fail(RTB_ERR_INVALID, "rtb_render: zero width/height/max_depth");
+	if (p->sample_end < p->sample_begin) return fail(RTB_ERR_INVALID, "rtb_render: sample_end < sample_begin");
+	uint32_t row_begin = p->row_begin, row_end = p->row_end;
+	if (row_begin == 0 && row_end == 0) row_end = p->height;
+	if (row_end > p->height || row_begin >= row_end) return fail(RTB_ERR_INVALID, "rtb_render: bad row range");
+	if ((uint64_t)p->width * p->height >= (1ull << 31)) return fail(RTB_ERR_INVALID, "rtb_render: image too large");
+	CUDA_TRY(cudaSetDevice(r->device));
+	int rc = ensure_framebuffer(r, p->width, p->height);
+	if (rc) return rc;
+
+	const uint32_t spp = p->sample_end - p->sample_begin;
+	const uint64_t npix = (uint64_t)p->width * (row_end - row_begin);
+	uint64_t target_paths = 8ull << 20;
+	if (const char* e = getenv("RTB_BATCH_PATHS")) { uint64_t v = strtoull(e, nullptr, 10); if (v > 0) target_paths = v; }
+	uint64_t S = p->samples_per_batch ? p->samples_per_batch : target_paths / npix;
+	if (S < 1) S = 1;
+	if (S > spp) S = spp ? spp : 1;
+	if (npix * S >= (1ull << 31)) return fail(RTB_ERR_INVALID, "rtb_render: batch too large (lower samples_per_batch)");
+	rc = ensure_wave(r, (size_t)(npix * S), p->max_depth);
+	if (rc) return rc;
+
+	BatchParams bp{};
+	bp.width = p->width; bp.height = p->height; bp.row_begin = row_begin; bp.n_rows = row_end - row_begin;
+	bp.npix = (uint32_t)npix; bp.sample_begin = p->sample_begin; bp.sample_end = p->sample_end;
+	bp.samples_per_batch = (uint32_t)S; bp.max_depth = p->max_depth; bp.seed = p->seed;
+	bp.variance = (p->flags & RTB_RENDER_VARIANCE) ? 1u : 0u;
+
+	cudaStream_t us = static_cast<cudaStream_t>(user_stream);
+	cudaStream_t st = r->stream;
+	// order this render after whatever the caller queued on its stream
+	CUDA_TRY(cudaEventRecord(r->ev_in, us));
+	CUDA_TRY(cudaStreamWaitEvent(st, r->ev_in, 0));
+	if (p->flags & RTB_RENDER_CLEAR) {
+		size_t bytes = (size_t)p->width * p->height * sizeof(float4);
+		CUDA_TRY(cudaMemsetAsync(r->d_accum, 0, bytes, st));
+		CUDA_TRY(cudaMemsetAsync(r->d_accum2, 0, bytes, st));
+	}
+	CUDA_TRY(cudaMemsetAsync(r->wv.batch_index, 0, sizeof(uint32_t), st));
+	CUDA_TRY(cudaEventRecord(r->ev_t0, st));
+
+	const uint32_t n_batches = spp ? (uint32_t)((spp + S - 1) / S) : 0;
+	const uint64_t launches_per_batch = 3 + 2ull * bp.max_depth;
+	const bool use_graph = getenv("RTB_NO_GRAPH") == nullptr && n_batches > 0;
+	if (use_graph) {
+		bool reuse = r->graph_valid && memcmp(&r->graph_bp, &bp, sizeof bp) == 0 && memcmp(&r->graph_cam, &r->cam, sizeof r->cam) == 0 &&
+		             r->graph_scene_version == r->scene_version && r->graph_accum == r->d_accum;
+		if (!reuse) {
+			free_graph(r);
+			cudaGraph_t graph = nullptr;
+			CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+			enqueue_batch(r, bp, st);
+			cudaError_t e = cudaStreamEndCapture(st, &graph);
+			if (e != cudaSuccess) return fail(RTB_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+			e = cudaGraphInstantiate(&r->graph_exec, graph, 0);
+			cudaGraphDestroy(graph);
+			if (e != cudaSuccess) return fail(RTB_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+			r->graph_bp = bp; r->graph_cam = r->cam; r->graph_scene_version = r->scene_version; r->graph_accum = r->d_accum;
+			r->graph_valid = true;
+		}
+		for (uint32_t b = 0; b < n_batches; ++b) CUDA_TRY(cudaGraphLaunch(r->graph_exec, st));
+	} else {
+		for (uint32_t b = 0; b < n_batches; ++b) enqueue_batch(r, bp, st);
+	}
+	CUDA_TRY(cudaGetLastError());
+	r->launches += launches_per_batch * n_batches;
+	r->batches += n_batches;
+	CUDA_TRY(cudaEventRecord(r->ev_t1, st));
+	r->timed = true;
+	// ... and let the caller's stream see the result
+	CUDA_TRY(cudaEventRecord(r->ev_out, st));
+	CUDA_TRY(cudaStreamWaitEvent(us, r->ev_out, 0));
+	return RTB_OK;
+}
+
+int rtb_synchronize(rtb_renderer* r) {
+	if (!r) return fail(RTB_ERR_INVALID, "rtb_synchronize: null renderer");
+	CUDA_TRY(cudaSetDevice(r->device));
+	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	return RTB_OK;
+}
+
+void* rtb_renderer_accum_ptr(rtb_renderer* r) { return r ? r->d_accum : nullptr; }
+void* rtb_renderer_accum2_ptr(rtb_renderer* r) { return r ? r->d_accum2 : nullptr; }
+
+int rtb_resolve(rtb_renderer* r, void* d_out, void* user_stream) {
+	if (!r || !r->d_accum) return fail(RTB_ERR_STATE, "rtb_resolve: nothing rendered");
+	CUDA_TRY(cudaSetDevice(r->device));
+	cudaStream_t us = static_cast<cudaStream_t>(user_stream);
+	CUDA_TRY(cudaEventRecord(r->ev_in, us));
+	CUDA_TRY(cudaStreamWaitEvent(r->stream, r->ev_in, 0));
+	launch_resolve(r->d_accum, d_out ? static_cast<float4*>(d_out) : r->d_out, r->width * r->height, r->stream);
+	r->launches += 1;
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaEventRecord(r->ev_out, r->stream));
+	CUDA_TRY(cudaStreamWaitEvent(us, r->ev_out, 0));
+	return RTB_OK;
+}
+
+int rtb_download(rtb_renderer* r, float* host_rgba) {
+	if (!r || !host_rgba) return fail(RTB_ERR_INVALID, "rtb_download: null argument");
+	int rc = rtb_resolve(r, nullptr, nullptr);
+	if (rc) return rc;
+	CUDA_TRY(cudaMemcpyAsync(host_rgba, r->d_out, (size_t)r->width * r->height * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
+	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	return RTB_OK;
+}
+
+int rtb_download_accum(rtb_renderer* r, float* host_sum, float* host_sum2) {
+	if (!r || !r->d_accum) return fail(RTB_ERR_STATE, "rtb_download_accum: nothing rendered");
+	CUDA_TRY(cudaSetDevice(r->device));
+	size_t bytes = (size_t)r->width * r->height * sizeof(float4);
+	if (host_sum) CUDA_TRY(cudaMemcpyAsync(host_sum, r->d_accum, bytes, cudaMemcpyDeviceToHost, r->stream));
+	if (host_sum2) CUDA_TRY(cudaMemcpyAsync(host_sum2, r->d_accum2, bytes, cudaMemcpyDeviceToHost, r->stream));
+	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	return RTB_OK;
+}
+
+int rtb_get_counters(rtb_renderer* r, rtb_counters* out) {
+	if (!r || !out) return fail(RTB_ERR_INVALID, "rtb_get_counters: null argument");
+	memset(out, 0, sizeof *out);
+	CUDA_TRY(cudaSetDevice(r->device));
+	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	if (r->d_wave) {
+		unsigned long long tot[2] = {0, 0};
+		CUDA_TRY(cudaMemcpy(tot, r->wv.totals, sizeof tot, cudaMemcpyDeviceToHost));
+		out->paths = tot[0]; out->rays = tot[1];
+	}
+	out->launches = r->launches; out->batches = r->batches;
+	if (r->timed) { float ms = 0.0f; if (cudaEventElapsedTime(&ms, r->ev_t0, r->ev_t1) == cudaSuccess) out->render_ms = ms; else cudaGetLastError(); }
+	return RTB_OK;
+}
+
+int rtb_reset_counters(rtb_renderer* r) {
+	if (!r) return fail(RTB_ERR_INVALID, "rtb_reset_counters: null renderer");
+	CUDA_TRY(cudaSetDevice(r->device));
+	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	if (r->d_wave) CUDA_TRY(cudaMemset(r->wv.totals, 0, 2 * sizeof(unsigned long long)));
+	r->launches = 0; r->batches = 0;
+	return RTB_OK;
+}
+
+int rtb_trace_rays(rtb_renderer* r, const rtb_ray* rays, size_t n, rtb_hit* hits_out) {
+	if (!r || (n && (!rays || !hits_out))) return fail(RTB_ERR_INVALID, "rtb_trace_rays: null argument");
+	if (!r->has_scene) return fail(RTB_ERR_STATE, "rtb_trace_rays: no scene");
+	if (n == 0) return RTB_OK;
+	if (n >= (1ull << 31)) return fail(RTB_ERR_INVALID, "rtb_trace_rays: too many rays");
+	CUDA_TRY(cudaSetDevice(r->device));
+	std::vector<float4> ho(n), hd(n);
+	for (size_t i = 0; i < n; ++i) {
+		ho[i] = make_float4(rays[i].o[0], rays[i].o[1], rays[i].o[2], rays[i].time);
+		hd[i] = make_float4(rays[i].d[0], rays[i].d[1], rays[i].d[2], 0.0f);
+	}
+	float4 *d_o = nullptr, *d_d = nullptr; int2* d_hit = nullptr; rtb_hit* d_rec = nullptr; uint32_t* d_cnt = nullptr;
+	int rc = RTB_OK;
+	auto cleanup = [&]() { cudaFree(d_o); cudaFree(d_d); cudaFree(d_hit); cudaFree(d_rec); cudaFree(d_cnt); };
+#define TRY_OR_CLEAN(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(RTB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+	TRY_OR_CLEAN(cudaMalloc(&d_o, n * 16));
+	TRY_OR_CLEAN(cudaMalloc(&d_d, n * 16));
+	TRY_OR_CLEAN(cudaMalloc(&d_hit, n * 8));
+	TRY_OR_CLEAN(cudaMalloc(&d_rec, n * sizeof(rtb_hit)));
+	TRY_OR_CLEAN(cudaMalloc(&d_cnt, 256));
+	TRY_OR_CLEAN(cudaMemcpyAsync(d_o, ho.data(), n * 16, cudaMemcpyHostToDevice, r->stream));
+	TRY_OR_CLEAN(cudaMemcpyAsync(d_d, hd.data(), n * 16, cudaMemcpyHostToDevice, r->stream));
+	launch_trace_rays(r->sv, d_o, d_d, (uint32_t)n, d_hit, d_rec, d_cnt, r->lc, r->stream);
+	r->launches += 2;
+	TRY_OR_CLEAN(cudaGetLastError());
+	TRY_OR_CLEAN(cudaMemcpyAsync(hits_out, d_rec, n * sizeof(rtb_hit), cudaMemcpyDeviceToHost, r->stream));
+	TRY_OR_CLEAN(cudaStreamSynchronize(r->stream));
+#undef TRY_OR_CLEAN
+	cleanup();
+	return rc;
+}
+
+}  // extern "C"

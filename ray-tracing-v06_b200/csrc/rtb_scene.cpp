@@ -1,0 +1,871 @@
+// rtb_scene.cpp — host side of the C ABI: scene graph, serialisation, the reference's BVH
+// builders restated, and the flattener that bakes instances into world-space SoA records.
+//
+// Reference behaviour followed (paths relative to the reference checkout):
+//   bounds         getSphereBounds / getMovingSphereBounds   main/src/rt_engine/geometry/SphereHittable.cu:52-54,85-89
+//   aabb           union, longest_axis, surface_area, centeroid   main/src/rt_engine/geometry/aabb.cuh:17-68
+//   BVH builders   BVH_Handle::Factory                        main/src/rt_engine/geometry/BVH.cu:166-383
+//   cameras        Pinhole/DefocusBlur/MotionBlurCamera ctors main/src/rt_engine/shaders/cu_Cameras.cuh:15-25,39-52,73-85
+// Quads, boxes, instances, media follow "Ray Tracing: The Next Week" (SURVEY.md App. B).
+#include "rtb_scene.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <functional>
+
+#include "rtmath.h"
+
+namespace rtb {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+
+}  // namespace rtb
+
+using namespace rtb;
+
+// ============================================================== small helpers
+
+static Box3 empty_box() {  // aabb() : min(1e9f), max(-1e9f)   aabb.cuh:17
+	Box3 b; for (int i = 0; i < 3; ++i) { b.mn[i] = 1e9f; b.mx[i] = -1e9f; } return b;
+}
+static void grow(Box3& a, const Box3& b) {  // operator+=  aabb.cuh:24  (glm::min/max: (y<x)?y:x / (x<y)?y:x)
+	for (int i = 0; i < 3; ++i) {
+		a.mn[i] = (b.mn[i] < a.mn[i]) ? b.mn[i] : a.mn[i];
+		a.mx[i] = (a.mx[i] < b.mx[i]) ? b.mx[i] : a.mx[i];
+	}
+}
+static Box3 box_of_points(const float (*p)[3], int n) {
+	Box3 b; for (int i = 0; i < 3; ++i) { b.mn[i] = p[0][i]; b.mx[i] = p[0][i]; }
+	for (int k = 1; k < n; ++k) for (int i = 0; i < 3; ++i) {
+		b.mn[i] = std::min(b.mn[i], p[k][i]); b.mx[i] = std::max(b.mx[i], p[k][i]);
+	}
+	return b;
+}
+static void pad_to_minimum(Box3& b) {  // book: aabb::pad_to_minimums, delta = 1e-4
+	const float delta = 0.0001f;
+	for (int i = 0; i < 3; ++i) if (b.mx[i] - b.mn[i] < delta) { b.mn[i] -= delta * 0.5f; b.mx[i] += delta * 0.5f; }
+}
+static int longest_axis(const Box3& b) {  // aabb.cuh:46-53
+	float sx = std::fabs(b.mx[0] - b.mn[0]), sy = std::fabs(b.mx[1] - b.mn[1]), sz = std::fabs(b.mx[2] - b.mn[2]);
+	if (sx > sy) return sx > sz ? 0 : 2;
+	return sy > sz ? 1 : 2;
+}
+static float surface_area(const Box3& b) {  // aabb.cuh:55-64
+	float sx = b.mx[0] - b.mn[0], sy = b.mx[1] - b.mn[1], sz = b.mx[2] - b.mn[2];
+	if (sx < 0 || sy < 0 || sz < 0) return 0.0f;
+	float cost = 0.0f; cost += sx * sy; cost += sx * sz; cost += sy * sz;
+	return 2.0f * cost;
+}
+
+// World-from-object transform: rotation about +y by (c,s) then translation.
+struct Xf {
+	float c = 1.0f, s = 0.0f, off[3] = {0, 0, 0};
+	bool rot = false, tr = false;
+	void point(const float in[3], float out[3]) const {
+		float x = in[0], y = in[1], z = in[2];
+		if (rot) { float nx = fmaf(c, x, s * z); float nz = fmaf(c, z, -(s * x)); x = nx; z = nz; }
+		if (tr) { x += off[0]; y += off[1]; z += off[2]; }
+		out[0] = x; out[1] = y; out[2] = z;
+	}
+	void vec(const float in[3], float out[3]) const {
+		float x = in[0], y = in[1], z = in[2];
+		if (rot) { float nx = fmaf(c, x, s * z); float nz = fmaf(c, z, -(s * x)); x = nx; z = nz; }
+		out[0] = x; out[1] = y; out[2] = z;
+	}
+};
+
+// ============================================================== C ABI: scene assembly
+
+extern "C" {
+
+int rtb_abi_version(void) { return RTB_ABI_VERSION; }
+const char* rtb_last_error(void) { return g_last_error.c_str(); }
+
+int rtb_scene_create(rtb_scene** out) {
+	if (!out) return fail(RTB_ERR_INVALID, "rtb_scene_create: null out");
+	*out = new rtb_scene();
+	return RTB_OK;
+}
+void rtb_scene_destroy(rtb_scene* s) { delete s; }
+
+static bool tex_ok(const rtb_scene* s, int t) { return t >= 0 && t < (int)s->textures.size(); }
+static bool mat_ok(const rtb_scene* s, int m) { return m >= 0 && m < (int)s->materials.size(); }
+static bool obj_ok(const rtb_scene* s, int o) { return o >= 0 && o < (int)s->objects.size(); }
+
+static int push_texture(rtb_scene* s, const rtbs_texture& t) { s->textures.push_back(t); return (int)s->textures.size() - 1; }
+
+int rtb_add_solid_texture(rtb_scene* s, const float rgb[3]) {
+	if (!s || !rgb) return fail(RTB_ERR_INVALID, "rtb_add_solid_texture: null argument");
+	rtbs_texture t{}; t.kind = RTB_TEX_SOLID; t.even = t.odd = -1; t.scale = 1.0f;
+	t.rgb[0] = rgb[0]; t.rgb[1] = rgb[1]; t.rgb[2] = rgb[2];
+	return push_texture(s, t);
+}
+int rtb_add_checker_texture(rtb_scene* s, float scale, int even_tex, int odd_tex) {
+	if (!s || !tex_ok(s, even_tex) || !tex_ok(s, odd_tex)) return fail(RTB_ERR_INVALID, "rtb_add_checker_texture: bad texture id");
+	if (!(scale != 0.0f)) return fail(RTB_ERR_INVALID, "rtb_add_checker_texture: scale must be non-zero");
+	rtbs_texture t{}; t.kind = RTB_TEX_CHECKER; t.even = even_tex; t.odd = odd_tex; t.scale = scale;
+	return push_texture(s, t);
+}
+int rtb_add_image_texture(rtb_scene* s, const uint8_t* px, int w, int h, int ch) {
+	if (!s || !px || w <= 0 || h <= 0 || !(ch == 1 || ch == 3 || ch == 4))
+		return fail(RTB_ERR_INVALID, "rtb_add_image_texture: bad image");
+	rtbs_texture t{}; t.kind = RTB_TEX_IMAGE; t.even = t.odd = -1; t.scale = 1.0f; t.width = w; t.height = h;
+	while (s->blob.size() % 4) s->blob.push_back(0);
+	t.blob_offset = (uint32_t)s->blob.size();
+	s->blob.resize(s->blob.size() + (size_t)w * h * 3);
+	uint8_t* dst = s->blob.data() + t.blob_offset;
+	for (size_t i = 0; i < (size_t)w * h; ++i) {
+		if (ch == 1) { dst[3 * i] = dst[3 * i + 1] = dst[3 * i + 2] = px[i]; }
+		else { dst[3 * i] = px[ch * i]; dst[3 * i + 1] = px[ch * i + 1]; dst[3 * i + 2] = px[ch * i + 2]; }
+	}
+	return push_texture(s, t);
+}
+int rtb_add_noise_texture(rtb_scene* s, float scale, uint32_t seed) {
+	if (!s) return fail(RTB_ERR_INVALID, "rtb_add_noise_texture: null scene");
+	rtbs_texture t{}; t.kind = RTB_TEX_NOISE; t.even = t.odd = -1; t.scale = scale; t.seed = seed;
+	while (s->blob.size() % 4) s->blob.push_back(0);
+	t.blob_offset = (uint32_t)s->blob.size();
+	s->blob.resize(s->blob.size() + RTBS_PERLIN_BYTES);
+	float* grad = reinterpret_cast<float*>(s->blob.data() + t.blob_offset);
+	int32_t* perm = reinterpret_cast<int32_t*>(s->blob.data() + t.blob_offset + 256 * 3 * 4);
+	// book perlin(): randvec[i] = unit_vector(random(-1,1)^3); three Fisher-Yates shuffles.
+	const uint32_t key1 = 0x5045524Cu;  // "PERL"
+	for (uint32_t i = 0; i < 256; ++i) {
+		rt::u4 c; c.x = i; c.y = 0; c.z = 0; c.w = 0;
+		rt::u4 r = rt::philox4x32_10(c, seed, key1);
+		float x = 2.0f * rt::uniform01(r.x) - 1.0f, y = 2.0f * rt::uniform01(r.y) - 1.0f, z = 2.0f * rt::uniform01(r.z) - 1.0f;
+		float len = std::sqrt(x * x + y * y + z * z);
+		if (!(len > 0.0f)) { x = 1.0f; y = z = 0.0f; len = 1.0f; }
+		grad[3 * i] = x / len; grad[3 * i + 1] = y / len; grad[3 * i + 2] = z / len;
+	}
+	for (uint32_t tbl = 0; tbl < 3; ++tbl) {
+		int32_t* p = perm + 256 * tbl;
+		for (int i = 0; i < 256; ++i) p[i] = i;
+		for (int i = 255; i > 0; --i) {
+			rt::u4 c; c.x = (uint32_t)i; c.y = 1 + tbl; c.z = 0; c.w = 0;
+			rt::u4 r = rt::philox4x32_10(c, seed, key1);
+			int target = (int)(((uint64_t)r.x * (uint64_t)(i + 1)) >> 32);  // uniform int in [0,i]
+			std::swap(p[i], p[target]);
+		}
+	}
+	return push_texture(s, t);
+}
+
+static int push_material(rtb_scene* s, int kind, int tex, const float a[3], float param) {
+	rtbs_material m{}; m.kind = kind; m.tex = tex; m.param = param;
+	m.albedo[0] = a ? a[0] : 1.0f; m.albedo[1] = a ? a[1] : 1.0f; m.albedo[2] = a ? a[2] : 1.0f;
+	s->materials.push_back(m); return (int)s->materials.size() - 1;
+}
+int rtb_add_lambertian(rtb_scene* s, int tex) {
+	if (!s || !tex_ok(s, tex)) return fail(RTB_ERR_INVALID, "rtb_add_lambertian: bad texture id");
+	return push_material(s, RTB_MAT_LAMBERTIAN, tex, nullptr, 0.0f);
+}
+int rtb_add_lambertian_color(rtb_scene* s, const float albedo[3]) {
+	if (!s || !albedo) return fail(RTB_ERR_INVALID, "rtb_add_lambertian_color: null argument");
+	return push_material(s, RTB_MAT_LAMBERTIAN, -1, albedo, 0.0f);
+}
+int rtb_add_metal(rtb_scene* s, const float albedo[3], float fuzz) {
+	if (!s || !albedo) return fail(RTB_ERR_INVALID, "rtb_add_metal: null argument");
+	return push_material(s, RTB_MAT_METAL, -1, albedo, fuzz);   // fuzz not clamped: cu_materials.cuh:75
+}
+int rtb_add_dielectric(rtb_scene* s, const float albedo[3], float ior) {
+	if (!s || !albedo) return fail(RTB_ERR_INVALID, "rtb_add_dielectric: null argument");
+	return push_material(s, RTB_MAT_DIELECTRIC, -1, albedo, ior);
+}
+int rtb_add_diffuse_light(rtb_scene* s, int tex) {
+	if (!s || !tex_ok(s, tex)) return fail(RTB_ERR_INVALID, "rtb_add_diffuse_light: bad texture id");
+	return push_material(s, RTB_MAT_DIFFUSE_LIGHT, tex, nullptr, 0.0f);
+}
+int rtb_add_isotropic(rtb_scene* s, int tex) {
+	if (!s || !tex_ok(s, tex)) return fail(RTB_ERR_INVALID, "rtb_add_isotropic: bad texture id");
+	return push_material(s, RTB_MAT_ISOTROPIC, tex, nullptr, 0.0f);
+}
+
+static int push_object(rtb_scene* s, const rtbs_object& o) { s->objects.push_back(o); return (int)s->objects.size() - 1; }
+static rtbs_object blank_object(int kind, int mat) {
+	rtbs_object o{}; o.kind = kind; o.mat = mat; o.child_begin = 0; o.child_count = 0; o.aux = 0; return o;
+}
+
+int rtb_add_sphere(rtb_scene* s, const float c[3], float r, int mat) {
+	if (!s || !c || !mat_ok(s, mat)) return fail(RTB_ERR_INVALID, "rtb_add_sphere: bad argument");
+	rtbs_object o = blank_object(RTB_OBJ_SPHERE, mat);
+	o.f[0] = c[0]; o.f[1] = c[1]; o.f[2] = c[2]; o.f[3] = r;
+	return push_object(s, o);
+}
+int rtb_add_moving_sphere(rtb_scene* s, const float c0[3], const float c1[3], float r, int mat) {
+	if (!s || !c0 || !c1 || !mat_ok(s, mat)) return fail(RTB_ERR_INVALID, "rtb_add_moving_sphere: bad argument");
+	rtbs_object o = blank_object(RTB_OBJ_MOVING_SPHERE, mat);
+	o.f[0] = c0[0]; o.f[1] = c0[1]; o.f[2] = c0[2]; o.f[3] = r; o.f[4] = c1[0]; o.f[5] = c1[1]; o.f[6] = c1[2];
+	return push_object(s, o);
+}
+static int add_planar(rtb_scene* s, int kind, const float Q[3], const float u[3], const float v[3], int mat) {
+	if (!s || !Q || !u || !v || !mat_ok(s, mat)) return fail(RTB_ERR_INVALID, "rtb_add_quad/triangle: bad argument");
+	rtbs_object o = blank_object(kind, mat);
+	for (int i = 0; i < 3; ++i) { o.f[i] = Q[i]; o.f[3 + i] = u[i]; o.f[6 + i] = v[i]; }
+	return push_object(s, o);
+}
+int rtb_add_quad(rtb_scene* s, const float Q[3], const float u[3], const float v[3], int mat) { return add_planar(s, RTB_OBJ_QUAD, Q, u, v, mat); }
+int rtb_add_triangle(rtb_scene* s, const float Q[3], const float u[3], const float v[3], int mat) { return add_planar(s, RTB_OBJ_TRIANGLE, Q, u, v, mat); }
+int rtb_add_box(rtb_scene* s, const float a[3], const float b[3], int mat) {
+	if (!s || !a || !b || !mat_ok(s, mat)) return fail(RTB_ERR_INVALID, "rtb_add_box: bad argument");
+	rtbs_object o = blank_object(RTB_OBJ_BOX, mat);
+	for (int i = 0; i < 3; ++i) { o.f[i] = std::fmin(a[i], b[i]); o.f[3 + i] = std::fmax(a[i], b[i]); }
+	return push_object(s, o);
+}
+static int add_group(rtb_scene* s, int kind, const int* ch, int n, int aux) {
+	if (!s || n < 0 || (n > 0 && !ch)) return fail(RTB_ERR_INVALID, "rtb_add_list/bvh: bad argument");
+	for (int i = 0; i < n; ++i) if (!obj_ok(s, ch[i])) return fail(RTB_ERR_INVALID, "rtb_add_list/bvh: bad child id");
+	rtbs_object o = blank_object(kind, -1);
+	o.child_begin = (int)s->children.size(); o.child_count = n; o.aux = aux;
+	s->children.insert(s->children.end(), ch, ch + n);
+	return push_object(s, o);
+}
+int rtb_add_list(rtb_scene* s, const int* ch, int n) { return add_group(s, RTB_OBJ_LIST, ch, n, 0); }
+int rtb_add_bvh(rtb_scene* s, const int* ch, int n, int builder) {
+	if (builder < RTB_BVH_TOPDOWN_MEDIAN || builder > RTB_BVH_BOTTOMUP) return fail(RTB_ERR_INVALID, "rtb_add_bvh: bad builder");
+	if (n < 1) return fail(RTB_ERR_INVALID, "rtb_add_bvh: needs at least one child");
+	return add_group(s, RTB_OBJ_BVH, ch, n, builder);
+}
+int rtb_add_translate(rtb_scene* s, int child, const float off[3]) {
+	if (!s || !off || !obj_ok(s, child)) return fail(RTB_ERR_INVALID, "rtb_add_translate: bad argument");
+	rtbs_object o = blank_object(RTB_OBJ_TRANSLATE, -1);
+	o.child_begin = (int)s->children.size(); o.child_count = 1; s->children.push_back(child);
+	o.f[0] = off[0]; o.f[1] = off[1]; o.f[2] = off[2];
+	return push_object(s, o);
+}
+int rtb_add_rotate_y(rtb_scene* s, int child, float degrees) {
+	if (!s || !obj_ok(s, child)) return fail(RTB_ERR_INVALID, "rtb_add_rotate_y: bad argument");
+	rtbs_object o = blank_object(RTB_OBJ_ROTATE_Y, -1);
+	o.child_begin = (int)s->children.size(); o.child_count = 1; s->children.push_back(child);
+	float radians = degrees * 0.01745329251994329576923690768489f;  // glm::radians
+	o.f[0] = degrees; o.f[1] = sinf(radians); o.f[2] = cosf(radians);
+	return push_object(s, o);
+}
+int rtb_add_constant_medium(rtb_scene* s, int boundary, float density, int phase_mat) {
+	if (!s || !obj_ok(s, boundary) || !mat_ok(s, phase_mat)) return fail(RTB_ERR_INVALID, "rtb_add_constant_medium: bad argument");
+	if (!(density > 0.0f)) return fail(RTB_ERR_INVALID, "rtb_add_constant_medium: density must be > 0");
+	rtbs_object o = blank_object(RTB_OBJ_CONSTANT_MEDIUM, phase_mat);
+	o.child_begin = (int)s->children.size(); o.child_count = 1; s->children.push_back(boundary);
+	o.f[0] = density; o.f[1] = -1.0f / density;
+	return push_object(s, o);
+}
+int rtb_scene_set_root(rtb_scene* s, int object) {
+	if (!s || !obj_ok(s, object)) return fail(RTB_ERR_INVALID, "rtb_scene_set_root: bad object id");
+	s->root = object; return RTB_OK;
+}
+int rtb_scene_set_background(rtb_scene* s, int mode, const float rgb[3]) {
+	if (!s || (mode != RTB_BG_SKY_GRADIENT && mode != RTB_BG_CONSTANT)) return fail(RTB_ERR_INVALID, "rtb_scene_set_background: bad mode");
+	s->background_mode = mode;
+	if (rgb) { s->background[0] = rgb[0]; s->background[1] = rgb[1]; s->background[2] = rgb[2]; }
+	return RTB_OK;
+}
+int rtb_scene_num_objects(const rtb_scene* s) { return s ? (int)s->objects.size() : RTB_ERR_INVALID; }
+
+}  // extern "C"
+
+// ============================================================== bounds
+
+static void quad_corners(const float* f, float p[4][3]) {
+	for (int i = 0; i < 3; ++i) { p[0][i] = f[i]; p[1][i] = f[i] + f[3 + i]; p[2][i] = f[i] + f[6 + i]; p[3][i] = f[i] + f[3 + i] + f[6 + i]; }
+}
+
+// Bounds of `obj` in its parent's frame.
+static int object_bounds(const rtb_scene* s, int id, Box3& out, int depth = 0) {
+	if (depth > 64) return fail(RTB_ERR_INVALID, "object graph too deep / cyclic");
+	const rtbs_object& o = s->objects[id];
+	switch (o.kind) {
+	case RTB_OBJ_SPHERE:
+		for (int i = 0; i < 3; ++i) { out.mn[i] = o.f[i] - o.f[3]; out.mx[i] = o.f[i] + o.f[3]; }
+		return RTB_OK;
+	case RTB_OBJ_MOVING_SPHERE: {
+		Box3 b0, b1;
+		for (int i = 0; i < 3; ++i) { b0.mn[i] = o.f[i] - o.f[3]; b0.mx[i] = o.f[i] + o.f[3]; b1.mn[i] = o.f[4 + i] - o.f[3]; b1.mx[i] = o.f[4 + i] + o.f[3]; }
+		for (int i = 0; i < 3; ++i) { out.mn[i] = (b1.mn[i] < b0.mn[i]) ? b1.mn[i] : b0.mn[i]; out.mx[i] = (b0.mx[i] < b1.mx[i]) ? b1.mx[i] : b0.mx[i]; }
+		return RTB_OK;
+	}
+	case RTB_OBJ_QUAD: case RTB_OBJ_TRIANGLE: {
+		float p[4][3]; quad_corners(o.f, p);
+		out = box_of_points(p, o.kind == RTB_OBJ_QUAD ? 4 : 3); pad_to_minimum(out);
+		return RTB_OK;
+	}
+	case RTB_OBJ_BOX:
+		for (int i = 0; i < 3; ++i) { out.mn[i] = o.f[i]; out.mx[i] = o.f[3 + i]; }
+		pad_to_minimum(out);
+		return RTB_OK;
+	case RTB_OBJ_LIST: case RTB_OBJ_BVH: {
+		out = empty_box();
+		for (int k = 0; k < o.child_count; ++k) {
+			Box3 b; int rc = object_bounds(s, s->children[o.child_begin + k], b, depth + 1); if (rc) return rc;
+			grow(out, b);
+		}
+		return RTB_OK;
+	}
+	case RTB_OBJ_TRANSLATE: {
+		Box3 b; int rc = object_bounds(s, s->children[o.child_begin], b, depth + 1); if (rc) return rc;
+		for (int i = 0; i < 3; ++i) { out.mn[i] = b.mn[i] + o.f[i]; out.mx[i] = b.mx[i] + o.f[i]; }
+		return RTB_OK;
+	}
+	case RTB_OBJ_ROTATE_Y: {  // book rotate_y ctor: box of the 8 rotated corners
+		Box3 b; int rc = object_bounds(s, s->children[o.child_begin], b, depth + 1); if (rc) return rc;
+		float sn = o.f[1], cs = o.f[2];
+		float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+		for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) for (int k = 0; k < 2; ++k) {
+			float x = i ? b.mx[0] : b.mn[0], y = j ? b.mx[1] : b.mn[1], z = k ? b.mx[2] : b.mn[2];
+			float t[3] = {cs * x + sn * z, y, -sn * x + cs * z};
+			for (int c = 0; c < 3; ++c) { mn[c] = std::fmin(mn[c], t[c]); mx[c] = std::fmax(mx[c], t[c]); }
+		}
+		for (int c = 0; c < 3; ++c) { out.mn[c] = mn[c]; out.mx[c] = mx[c]; }
+		return RTB_OK;
+	}
+	case RTB_OBJ_CONSTANT_MEDIUM:
+		return object_bounds(s, s->children[o.child_begin], out, depth + 1);
+	}
+	return fail(RTB_ERR_INVALID, "unknown object kind");
+}
+
+extern "C" int rtb_object_bounds(const rtb_scene* s, int object, float out6[6]) {
+	if (!s || !out6 || !obj_ok(s, object)) return fail(RTB_ERR_INVALID, "rtb_object_bounds: bad argument");
+	Box3 b; int rc = object_bounds(s, object, b); if (rc) return rc;
+	for (int i = 0; i < 3; ++i) { out6[i] = b.mn[i]; out6[3 + i] = b.mx[i]; }
+	return RTB_OK;
+}
+
+// ============================================================== serialisation
+
+extern "C" size_t rtb_scene_serialize(const rtb_scene* s, void* buf, size_t cap) {
+	if (!s) return 0;
+	size_t need = sizeof(rtbs_header) + s->textures.size() * sizeof(rtbs_texture) + s->materials.size() * sizeof(rtbs_material) +
+	              s->objects.size() * sizeof(rtbs_object) + s->children.size() * 4 + s->blob.size();
+	if (!buf || cap < need) return need;
+	rtbs_header h{}; h.magic = RTBS_MAGIC; h.version = RTBS_VERSION;
+	h.n_textures = (uint32_t)s->textures.size(); h.n_materials = (uint32_t)s->materials.size();
+	h.n_objects = (uint32_t)s->objects.size(); h.n_children = (uint32_t)s->children.size();
+	h.n_blob_bytes = (uint32_t)s->blob.size(); h.root_object = s->root; h.background_mode = s->background_mode;
+	memcpy(h.background, s->background, 12);
+	uint8_t* p = static_cast<uint8_t*>(buf);
+	auto put = [&](const void* src, size_t n) { if (n) memcpy(p, src, n); p += n; };
+	put(&h, sizeof h);
+	put(s->textures.data(), s->textures.size() * sizeof(rtbs_texture));
+	put(s->materials.data(), s->materials.size() * sizeof(rtbs_material));
+	put(s->objects.data(), s->objects.size() * sizeof(rtbs_object));
+	put(s->children.data(), s->children.size() * 4);
+	put(s->blob.data(), s->blob.size());
+	return need;
+}
+
+// ============================================================== BVH builders (BVH.cu:166-383 restated)
+
+namespace rtb {
+
+namespace {
+struct Item { Box3 box; int idx; };
+
+struct Builder {
+	std::vector<Item> arr;
+	std::vector<rtb_bvh_node> nodes;
+
+	Box3 partition_bounds(int start, int end) const {  // _get_partition_bounds  BVH.cu:306-312
+		Box3 b = empty_box();
+		for (int i = start; i < end; ++i) grow(b, arr[i].box);
+		return b;
+	}
+	int push_node(const Box3& b, int left, int right) {
+		rtb_bvh_node n; memcpy(n.bmin, b.mn, 12); memcpy(n.bmax, b.mx, 12);
+		n.left_child_idx = left; n.right_child_hittable_idx = right;
+		nodes.push_back(n); return (int)nodes.size() - 1;
+	}
+	// _build_bvh_rec1  BVH.cu:180-210: sort the range by min[longest axis], split at the middle,
+	// children first (left, then right), node last => post-order array, root = last index.
+	int rec_median(int start, int end) {
+		Box3 bounds = partition_bounds(start, end);
+		int axis = longest_axis(bounds);
+		if (end - start == 1) return push_node(bounds, -1, start);
+		std::sort(arr.begin() + start, arr.begin() + end,
+		          [axis](const Item& a, const Item& b) { return a.box.mn[axis] < b.box.mn[axis]; });
+		int mid = (start + end) / 2;
+		int l = rec_median(start, mid);
+		int r = rec_median(mid, end);
+		return push_node(bounds, l, r);
+	}
+	// _find_optimal_split  BVH.cu:245-283: 16 planes x 3 axes on the partition bounds, cost = SA*count.
+	void find_split(int start, int end, const Box3& bounds, int& best_axis, float& best_split) const {
+		const int split_points = 16;
+		float best_cost = FLT_MAX;
+		for (int axis = 0; axis < 3; ++axis) for (int split = 0; split < split_points; ++split) {
+			float pos = (split + 1.0f) / (split_points + 1.0f);
+			float lo = bounds.mn[axis], hi = bounds.mx[axis];
+			pos = lo * (1.0f - pos) + hi * pos;  // glm::mix
+			Box3 lb = empty_box(), rb = empty_box(); int lc = 0, rc = 0;
+			for (int i = start; i < end; ++i) {
+				const Box3& b = arr[i].box;
+				float cen = (b.mx[axis] + b.mn[axis]) * 0.5f;  // centeroid  aabb.cuh:66-68
+				if (cen < pos) { grow(lb, b); lc++; } else { grow(rb, b); rc++; }
+			}
+			float cost = surface_area(lb) * lc + surface_area(rb) * rc;
+			if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = pos; }
+		}
+	}
+	// _partition_by_split  BVH.cu:285-304
+	int partition(int start, int end, int axis, float pos) {
+		int i = start, j = end;
+		while (i < j) {
+			const Box3& b = arr[i].box;
+			float cen = (b.mx[axis] + b.mn[axis]) * 0.5f;
+			if (cen < pos) i++; else std::swap(arr[i], arr[--j]);
+		}
+		return i;
+	}
+	// _build_bvh_rec2  BVH.cu:212-239.  The reference recurses forever when a split leaves one side
+	// empty; here such a range falls back to the median split (documented deviation).
+	int rec_sah(int start, int end) {
+		Box3 bounds = partition_bounds(start, end);
+		if (end - start == 1) return push_node(bounds, -1, start);
+		int axis = 0; float split = 0.0f;
+		find_split(start, end, bounds, axis, split);
+		int mid = partition(start, end, axis, split);
+		if (mid == start || mid == end) {
+			int ax = longest_axis(bounds);
+			std::sort(arr.begin() + start, arr.begin() + end,
+			          [ax](const Item& a, const Item& b) { return a.box.mn[ax] < b.box.mn[ax]; });
+			mid = (start + end) / 2;
+		}
+		int l = rec_sah(start, mid);
+		int r = rec_sah(mid, end);
+		return push_node(bounds, l, r);
+	}
+};
+}  // namespace
+
+static int build_bottom_up(const std::vector<Box3>& boxes, std::vector<rtb_bvh_node>& nodes, std::vector<int>& order, int& root) {
+	// BuildBVH_BottomUp  BVH.cu:315-383: leaves first in input order, then repeatedly merge the pair
+	// with the smallest surface_area(union) * hittable_count (first minimum in (a,b) scan order).
+	struct Work { Box3 box; int count; int node; };
+	std::vector<Work> work;
+	nodes.clear(); order.clear();
+	for (int i = 0; i < (int)boxes.size(); ++i) {
+		rtb_bvh_node n; memcpy(n.bmin, boxes[i].mn, 12); memcpy(n.bmax, boxes[i].mx, 12);
+		n.left_child_idx = -1; n.right_child_hittable_idx = i;
+		order.push_back(i);
+		work.push_back({boxes[i], 1, (int)nodes.size()});
+		nodes.push_back(n);
+	}
+	while (work.size() > 1) {
+		float best = FLT_MAX; int ai = 0, bi = 1;
+		for (int a = 0; a < (int)work.size(); ++a) for (int b = a + 1; b < (int)work.size(); ++b) {
+			Box3 u = work[a].box; grow(u, work[b].box);
+			float cost = surface_area(u) * (work[a].count + work[b].count);
+			if (cost < best) { ai = a; bi = b; best = cost; }
+		}
+		Box3 u = work[ai].box; grow(u, work[bi].box);
+		rtb_bvh_node n; memcpy(n.bmin, u.mn, 12); memcpy(n.bmax, u.mx, 12);
+		n.left_child_idx = work[ai].node; n.right_child_hittable_idx = work[bi].node;
+		Work merged{u, work[ai].count + work[bi].count, (int)nodes.size()};
+		work.erase(work.begin() + bi); work.erase(work.begin() + ai);
+		work.push_back(merged);
+		nodes.push_back(n);
+	}
+	root = work[0].node;
+	return (int)nodes.size();
+}
+
+int build_bvh(const std::vector<Box3>& boxes, int builder, std::vector<rtb_bvh_node>& nodes, std::vector<int>& order, int& root) {
+	if (boxes.empty()) return fail(RTB_ERR_INVALID, "build_bvh: no primitives");
+	if (builder == RTB_BVH_BOTTOMUP) return build_bottom_up(boxes, nodes, order, root);
+	Builder b; b.arr.resize(boxes.size());
+	for (int i = 0; i < (int)boxes.size(); ++i) { b.arr[i].box = boxes[i]; b.arr[i].idx = i; }
+	b.nodes.reserve(2 * boxes.size());
+	if (builder == RTB_BVH_TOPDOWN_MEDIAN) root = b.rec_median(0, (int)boxes.size());
+	else if (builder == RTB_BVH_TOPDOWN_SAH) root = b.rec_sah(0, (int)boxes.size());
+	else return fail(RTB_ERR_INVALID, "build_bvh: unknown builder");
+	nodes.swap(b.nodes);
+	order.resize(boxes.size());
+	for (int i = 0; i < (int)boxes.size(); ++i) order[i] = b.arr[i].idx;  // BVH.cu:174-177
+	return (int)nodes.size();
+}
+
+// Binned SAH over centroid bounds (32 bins), leaves of one primitive, depth-capped: the quality
+// builder for world BVHs that are not pinned to a reference topology.
+int build_bvh_world_sah(const std::vector<Box3>& boxes, std::vector<rtb_bvh_node>& nodes, std::vector<int>& order, int& root) {
+	if (boxes.empty()) return fail(RTB_ERR_INVALID, "build_bvh_world_sah: no primitives");
+	const int n = (int)boxes.size();
+	std::vector<int> idx(n); for (int i = 0; i < n; ++i) idx[i] = i;
+	std::vector<float> cen(3 * (size_t)n);
+	for (int i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) cen[3 * (size_t)i + a] = 0.5f * (boxes[i].mn[a] + boxes[i].mx[a]);
+	nodes.clear(); nodes.reserve(2 * (size_t)n);
+	auto push = [&](const Box3& b, int l, int r) {
+		rtb_bvh_node nd; memcpy(nd.bmin, b.mn, 12); memcpy(nd.bmax, b.mx, 12); nd.left_child_idx = l; nd.right_child_hittable_idx = r;
+		nodes.push_back(nd); return (int)nodes.size() - 1;
+	};
+	const int NB = 32, MAX_DEPTH = 26;
+	std::function<int(int, int, int)> rec = [&](int start, int end, int depth) -> int {
+		Box3 bounds = empty_box();
+		for (int i = start; i < end; ++i) grow(bounds, boxes[idx[i]]);
+		if (end - start == 1) return push(bounds, -1, start);
+		float cmn[3] = {INFINITY, INFINITY, INFINITY}, cmx[3] = {-INFINITY, -INFINITY, -INFINITY};
+		for (int i = start; i < end; ++i) for (int a = 0; a < 3; ++a) {
+			float c = cen[3 * (size_t)idx[i] + a]; cmn[a] = std::fmin(cmn[a], c); cmx[a] = std::fmax(cmx[a], c);
+		}
+		int best_axis = -1, best_bin = -1; float best_cost = INFINITY;
+		if (depth < MAX_DEPTH && end - start > 2) {
+			for (int a = 0; a < 3; ++a) {
+				float ext = cmx[a] - cmn[a];
+				if (!(ext > 0.0f)) continue;
+				Box3 bb[NB]; int bc[NB];
+				for (int b = 0; b < NB; ++b) { bb[b] = empty_box(); bc[b] = 0; }
+				float scale = NB / ext;
+				for (int i = start; i < end; ++i) {
+					int b = (int)((cen[3 * (size_t)idx[i] + a] - cmn[a]) * scale); if (b >= NB) b = NB - 1; if (b < 0) b = 0;
+					grow(bb[b], boxes[idx[i]]); bc[b]++;
+				}
+				float right_area[NB]; int right_cnt[NB];
+				Box3 acc = empty_box(); int cnt = 0;
+				for (int b = NB - 1; b > 0; --b) { grow(acc, bb[b]); cnt += bc[b]; right_area[b] = surface_area(acc); right_cnt[b] = cnt; }
+				acc = empty_box(); cnt = 0;
+				for (int b = 0; b < NB - 1; ++b) {
+					grow(acc, bb[b]); cnt += bc[b];
+					if (cnt == 0 || right_cnt[b + 1] == 0) continue;
+					float cost = surface_area(acc) * cnt + right_area[b + 1] * right_cnt[b + 1];
+					if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
+				}
+			}
+		}
+		int mid;
+		if (best_axis >= 0) {
+			float ext = cmx[best_axis] - cmn[best_axis], scale = NB / ext;
+			auto it = std::partition(idx.begin() + start, idx.begin() + end, [&](int id) {
+				int b = (int)((cen[3 * (size_t)id + best_axis] - cmn[best_axis]) * scale); if (b >= NB) b = NB - 1; if (b < 0) b = 0;
+				return b <= best_bin;
+			});
+			mid = (int)(it - idx.begin());
+		} else mid = start;
+		if (mid == start || mid == end) {  // degenerate: balanced median on the widest centroid axis
+			int ax = 0; float w = -1.0f;
+			for (int a = 0; a < 3; ++a) if (cmx[a] - cmn[a] > w) { w = cmx[a] - cmn[a]; ax = a; }
+			mid = (start + end) / 2;
+			std::nth_element(idx.begin() + start, idx.begin() + mid, idx.begin() + end, [&](int x, int y) {
+				float cx = cen[3 * (size_t)x + ax], cy = cen[3 * (size_t)y + ax];
+				return cx < cy || (cx == cy && x < y);
+			});
+		}
+		int l = rec(start, mid, depth + 1);
+		int r = rec(mid, end, depth + 1);
+		return push(bounds, l, r);
+	};
+	root = rec(0, n, 0);
+	order = idx;
+	return (int)nodes.size();
+}
+
+int bvh_depth(const std::vector<rtb_bvh_node>& nodes, int root) {
+	std::vector<std::pair<int, int>> st; st.push_back({root, 1}); int best = 0;
+	while (!st.empty()) {
+		auto [i, d] = st.back(); st.pop_back();
+		best = std::max(best, d);
+		if (nodes[i].left_child_idx != -1) { st.push_back({nodes[i].left_child_idx, d + 1}); st.push_back({nodes[i].right_child_hittable_idx, d + 1}); }
+	}
+	return best;
+}
+
+}  // namespace rtb
+
+extern "C" int rtb_bvh_build(const float* aabbs, int n, int builder, rtb_bvh_node* nodes_out, int* order_out, int* root_out) {
+	if (!aabbs || n <= 0 || !nodes_out || !order_out || !root_out) return fail(RTB_ERR_INVALID, "rtb_bvh_build: bad argument");
+	std::vector<Box3> boxes(n);
+	for (int i = 0; i < n; ++i) { memcpy(boxes[i].mn, aabbs + 6 * (size_t)i, 12); memcpy(boxes[i].mx, aabbs + 6 * (size_t)i + 3, 12); }
+	std::vector<rtb_bvh_node> nodes; std::vector<int> order; int root = -1;
+	int rc = build_bvh(boxes, builder, nodes, order, root);
+	if (rc < 0) return rc;
+	memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(rtb_bvh_node));
+	memcpy(order_out, order.data(), order.size() * sizeof(int));
+	*root_out = root;
+	return (int)nodes.size();
+}
+
+extern "C" int rtb_scene_world_bvh(const rtb_scene* s, rtb_bvh_node* nodes_out, int cap, int* root_out) {
+	if (!s) return fail(RTB_ERR_INVALID, "rtb_scene_world_bvh: null scene");
+	if (s->world_nodes.empty()) return fail(RTB_ERR_STATE, "rtb_scene_world_bvh: scene has not been flattened (rtb_renderer_set_scene / rtb_scene_flatten)");
+	if (nodes_out) {
+		if (cap < (int)s->world_nodes.size()) return fail(RTB_ERR_INVALID, "rtb_scene_world_bvh: buffer too small");
+		memcpy(nodes_out, s->world_nodes.data(), s->world_nodes.size() * sizeof(rtb_bvh_node));
+	}
+	if (root_out) *root_out = s->world_root;
+	return (int)s->world_nodes.size();
+}
+
+// ============================================================== flattener
+
+namespace rtb {
+
+namespace {
+struct Flattener {
+	rtb_scene& s;
+	FlatScene& out;
+	std::vector<Box3> prim_boxes;
+	std::string err;
+
+	void emit(int type, const DevPrim& p, const Box3& b, int mat, int obj) {
+		out.prims.push_back(p); out.prim_type.push_back(type);
+		DevPrimInfo pi; pi.material = mat; pi.object = obj; out.prim_info.push_back(pi);
+		prim_boxes.push_back(b);
+	}
+	void emit_sphere(const rtbs_object& o, int id, const Xf& x) {
+		float c[3]; x.point(o.f, c);
+		DevPrim p{}; p.q[0] = c[0]; p.q[1] = c[1]; p.q[2] = c[2]; p.q[3] = o.f[3];
+		p.q[4] = x.rot ? x.c : 1.0f; p.q[5] = x.rot ? x.s : 0.0f;   // instance rotation, for get_sphere_uv in the object frame
+		Box3 b; for (int i = 0; i < 3; ++i) { b.mn[i] = c[i] - o.f[3]; b.mx[i] = c[i] + o.f[3]; }
+		emit(PRIM_SPHERE, p, b, o.mat, id);
+	}
+	void emit_moving_sphere(const rtbs_object& o, int id, const Xf& x) {
+		float c0[3], c1[3]; x.point(o.f, c0); x.point(o.f + 4, c1);
+		DevPrim p{}; p.q[0] = c0[0]; p.q[1] = c0[1]; p.q[2] = c0[2]; p.q[3] = o.f[3]; p.q[4] = c1[0]; p.q[5] = c1[1]; p.q[6] = c1[2];
+		p.q[8] = x.rot ? x.c : 1.0f; p.q[9] = x.rot ? x.s : 0.0f;
+		Box3 b;
+		for (int i = 0; i < 3; ++i) {
+			float a0 = c0[i] - o.f[3], a1 = c1[i] - o.f[3], b0 = c0[i] + o.f[3], b1 = c1[i] + o.f[3];
+			b.mn[i] = (a1 < a0) ? a1 : a0; b.mx[i] = (b0 < b1) ? b1 : b0;
+		}
+		emit(PRIM_MOVING_SPHERE, p, b, o.mat, id);
+	}
+	void emit_planar(int type, const float Q0[3], const float u0[3], const float v0[3], int mat, int id, const Xf& x) {
+		float Q[3], u[3], v[3]; x.point(Q0, Q); x.vec(u0, u); x.vec(v0, v);
+		// book quad ctor: n = cross(u,v); normal = unit(n); D = dot(normal,Q); w = n / dot(n,n)
+		rt::v3 U = rt::mk(u[0], u[1], u[2]), V = rt::mk(v[0], v[1], v[2]), QQ = rt::mk(Q[0], Q[1], Q[2]);
+		rt::v3 n = rt::cross(U, V);
+		rt::v3 N = rt::normalize(n);
+		float D = rt::dot(N, QQ);
+		rt::v3 w = rt::divs(n, rt::dot(n, n));
+		DevPrim p{};
+		p.q[0] = Q[0]; p.q[1] = Q[1]; p.q[2] = Q[2]; p.q[3] = D;
+		p.q[4] = u[0]; p.q[5] = u[1]; p.q[6] = u[2]; p.q[7] = N.x;
+		p.q[8] = v[0]; p.q[9] = v[1]; p.q[10] = v[2]; p.q[11] = N.y;
+		p.q[12] = w.x; p.q[13] = w.y; p.q[14] = w.z; p.q[15] = N.z;
+		float f[9]; memcpy(f, Q, 12); memcpy(f + 3, u, 12); memcpy(f + 6, v, 12);
+		float pts[4][3]; quad_corners(f, pts);
+		Box3 b = box_of_points(pts, type == PRIM_QUAD ? 4 : 3); pad_to_minimum(b);
+		emit(type, p, b, mat, id);
+	}
+	void emit_box(const rtbs_object& o, int id, const Xf& x) {
+		// book box(a,b): six quads with outward normals (front, right, back, left, top, bottom)
+		const float* mn = o.f; const float* mx = o.f + 3;
+		float dx[3] = {mx[0] - mn[0], 0, 0}, dy[3] = {0, mx[1] - mn[1], 0}, dz[3] = {0, 0, mx[2] - mn[2]};
+		float ndx[3] = {-dx[0], 0, 0}, ndz[3] = {0, 0, -dz[2]};
+		float q0[3] = {mn[0], mn[1], mx[2]}; emit_planar(PRIM_QUAD, q0, dx, dy, o.mat, id, x);
+		float q1[3] = {mx[0], mn[1], mx[2]}; emit_planar(PRIM_QUAD, q1, ndz, dy, o.mat, id, x);
+		float q2[3] = {mx[0], mn[1], mn[2]}; emit_planar(PRIM_QUAD, q2, ndx, dy, o.mat, id, x);
+		float q3[3] = {mn[0], mn[1], mn[2]}; emit_planar(PRIM_QUAD, q3, dz, dy, o.mat, id, x);
+		float q4[3] = {mn[0], mx[1], mx[2]}; emit_planar(PRIM_QUAD, q4, dx, ndz, o.mat, id, x);
+		float q5[3] = {mn[0], mn[1], mn[2]}; emit_planar(PRIM_QUAD, q5, dx, dz, o.mat, id, x);
+	}
+	// Resolve a medium boundary: SPHERE or BOX under any chain of translate / rotate_y.
+	int emit_medium(const rtbs_object& med, int id, Xf x) {
+		int cur = s.children[med.child_begin];
+		for (int guard = 0; guard < 64; ++guard) {
+			const rtbs_object& o = s.objects[cur];
+			if (o.kind == RTB_OBJ_TRANSLATE) { x = compose_translate(x, o.f); cur = s.children[o.child_begin]; continue; }
+			if (o.kind == RTB_OBJ_ROTATE_Y) { x = compose_rotate(x, o.f[1], o.f[2]); cur = s.children[o.child_begin]; continue; }
+			int medium_index = out.n_media++;
+			if (o.kind == RTB_OBJ_SPHERE) {
+				float c[3]; x.point(o.f, c);
+				DevPrim p{}; p.q[0] = c[0]; p.q[1] = c[1]; p.q[2] = c[2]; p.q[3] = o.f[3]; p.q[4] = med.f[1];
+				p.q[5] = rt::u2f((uint32_t)medium_index);
+				Box3 b; for (int i = 0; i < 3; ++i) { b.mn[i] = c[i] - o.f[3]; b.mx[i] = c[i] + o.f[3]; }
+				emit(PRIM_MEDIUM_SPHERE, p, b, med.mat, id);
+				return RTB_OK;
+			}
+			if (o.kind == RTB_OBJ_BOX) {
+				DevPrim p{};
+				p.q[0] = o.f[0]; p.q[1] = o.f[1]; p.q[2] = o.f[2]; p.q[3] = x.c;
+				p.q[4] = o.f[3]; p.q[5] = o.f[4]; p.q[6] = o.f[5]; p.q[7] = x.s;
+				p.q[8] = x.off[0]; p.q[9] = x.off[1]; p.q[10] = x.off[2]; p.q[11] = med.f[1];
+				p.q[12] = rt::u2f((uint32_t)medium_index);
+				float pts[8][3]; int k = 0;
+				for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) for (int l = 0; l < 2; ++l) {
+					float c[3] = {i ? o.f[3] : o.f[0], j ? o.f[4] : o.f[1], l ? o.f[5] : o.f[2]};
+					x.point(c, pts[k++]);
+				}
+				Box3 b = box_of_points(pts, 8); pad_to_minimum(b);
+				emit(PRIM_MEDIUM_BOX, p, b, med.mat, id);
+				return RTB_OK;
+			}
+			return fail(RTB_ERR_UNSUPPORTED, "constant_medium boundary must be a sphere or a box (optionally under translate / rotate_y)");
+		}
+		return fail(RTB_ERR_INVALID, "constant_medium boundary chain too deep");
+	}
+	static Xf compose_translate(const Xf& x, const float off[3]) {
+		Xf r = x; float o[3]; x.point(off, o);  // world = X(p + off) => offset' = X(off)
+		r.off[0] = o[0]; r.off[1] = o[1]; r.off[2] = o[2]; r.tr = true; return r;
+	}
+	static Xf compose_rotate(const Xf& x, float sn, float cs) {
+		Xf r = x;
+		if (x.rot) { r.c = x.c * cs - x.s * sn; r.s = x.s * cs + x.c * sn; }
+		else { r.c = cs; r.s = sn; }
+		r.rot = true; return r;
+	}
+	int walk(int id, const Xf& x, int depth) {
+		if (depth > 64) return fail(RTB_ERR_INVALID, "object graph too deep / cyclic");
+		const rtbs_object& o = s.objects[id];
+		switch (o.kind) {
+		case RTB_OBJ_SPHERE: emit_sphere(o, id, x); return RTB_OK;
+		case RTB_OBJ_MOVING_SPHERE: emit_moving_sphere(o, id, x); return RTB_OK;
+		case RTB_OBJ_QUAD: emit_planar(PRIM_QUAD, o.f, o.f + 3, o.f + 6, o.mat, id, x); return RTB_OK;
+		case RTB_OBJ_TRIANGLE: emit_planar(PRIM_TRIANGLE, o.f, o.f + 3, o.f + 6, o.mat, id, x); return RTB_OK;
+		case RTB_OBJ_BOX: emit_box(o, id, x); return RTB_OK;
+		case RTB_OBJ_LIST: case RTB_OBJ_BVH:
+			for (int k = 0; k < o.child_count; ++k) { int rc = walk(s.children[o.child_begin + k], x, depth + 1); if (rc) return rc; }
+			return RTB_OK;
+		case RTB_OBJ_TRANSLATE: return walk(s.children[o.child_begin], compose_translate(x, o.f), depth + 1);
+		case RTB_OBJ_ROTATE_Y: return walk(s.children[o.child_begin], compose_rotate(x, o.f[1], o.f[2]), depth + 1);
+		case RTB_OBJ_CONSTANT_MEDIUM: return emit_medium(o, id, x);
+		}
+		return fail(RTB_ERR_INVALID, "unknown object kind");
+	}
+};
+}  // namespace
+
+int flatten(rtb_scene& s, FlatScene& out) {
+	if (s.root < 0) return fail(RTB_ERR_STATE, "scene has no root object (rtb_scene_set_root)");
+	out = FlatScene();
+	Flattener fl{s, out, {}, {}};
+	Xf ident;
+	int rc = fl.walk(s.root, ident, 0);
+	if (rc) return rc;
+	if (out.prims.empty()) return fail(RTB_ERR_INVALID, "scene has no primitives");
+	if (out.prims.size() >= (1u << 28)) return fail(RTB_ERR_UNSUPPORTED, "too many primitives");
+
+	// World BVH.  A root that is a reference BVH keeps the reference's builder (and therefore its
+	// exact node / primitive order); anything else gets the quality SAH builder.
+	const rtbs_object& root = s.objects[s.root];
+	std::vector<rtb_bvh_node> nodes; std::vector<int> order; int root_idx = -1;
+	const int STACK_LIMIT = 30;
+	bool built = false;
+	if (root.kind == RTB_OBJ_BVH) {
+		rc = build_bvh(fl.prim_boxes, root.aux, nodes, order, root_idx);
+		if (rc < 0) return rc;
+		built = bvh_depth(nodes, root_idx) <= STACK_LIMIT;
+	}
+	if (!built) {
+		rc = build_bvh_world_sah(fl.prim_boxes, nodes, order, root_idx);
+		if (rc < 0) return rc;
+		if (bvh_depth(nodes, root_idx) > STACK_LIMIT) {
+			rc = build_bvh(fl.prim_boxes, RTB_BVH_TOPDOWN_MEDIAN, nodes, order, root_idx);
+			if (rc < 0) return rc;
+		}
+	}
+	out.max_depth_nodes = bvh_depth(nodes, root_idx);
+
+	// Reorder primitives into BVH leaf order (Factory::hittables, BVH.cu:174-177).
+	{
+		std::vector<DevPrim> prims(out.prims.size()); std::vector<DevPrimInfo> info(out.prims.size()); std::vector<int32_t> type(out.prims.size());
+		for (size_t i = 0; i < order.size(); ++i) { prims[i] = out.prims[order[i]]; info[i] = out.prim_info[order[i]]; type[i] = out.prim_type[order[i]]; }
+		out.prims.swap(prims); out.prim_info.swap(info); out.prim_type.swap(type);
+	}
+	s.world_nodes = nodes; s.world_root = root_idx;
+
+	// Wide layout: one 64-byte record per inner node carrying both children's boxes, numbered in
+	// depth-first pre-order (root = 0) so the near part of a subtree is contiguous.
+	if (nodes[root_idx].left_child_idx == -1) {
+		int prim = nodes[root_idx].right_child_hittable_idx;
+		out.root_ref = make_leaf_ref(prim, out.prim_type[prim]);
+	} else {
+		std::vector<int> dev_index(nodes.size(), -1);
+		std::vector<int> stack; stack.push_back(root_idx); int next = 0;
+		std::vector<int> inner_order;
+		while (!stack.empty()) {
+			int i = stack.back(); stack.pop_back();
+			if (nodes[i].left_child_idx == -1) continue;
+			dev_index[i] = next++; inner_order.push_back(i);
+			stack.push_back(nodes[i].right_child_hittable_idx);
+			stack.push_back(nodes[i].left_child_idx);
+		}
+		out.nodes.resize(inner_order.size());
+		auto ref_of = [&](int i) {
+			if (nodes[i].left_child_idx == -1) { int prim = nodes[i].right_child_hittable_idx; return make_leaf_ref(prim, out.prim_type[prim]); }
+			return dev_index[i];
+		};
+		for (int i : inner_order) {
+			const rtb_bvh_node& l = nodes[nodes[i].left_child_idx];
+			const rtb_bvh_node& r = nodes[nodes[i].right_child_hittable_idx];
+			DevNode& d = out.nodes[dev_index[i]];
+			d.f[0] = l.bmin[0]; d.f[1] = l.bmin[1]; d.f[2] = l.bmin[2]; d.f[3] = l.bmax[0]; d.f[4] = l.bmax[1]; d.f[5] = l.bmax[2];
+			d.f[6] = r.bmin[0]; d.f[7] = r.bmin[1]; d.f[8] = r.bmin[2]; d.f[9] = r.bmax[0]; d.f[10] = r.bmax[1]; d.f[11] = r.bmax[2];
+			d.left = ref_of(nodes[i].left_child_idx); d.right = ref_of(nodes[i].right_child_hittable_idx); d.pad0 = d.pad1 = 0;
+		}
+		out.root_ref = 0;
+	}
+
+	// Materials / textures.
+	out.materials.resize(s.materials.size());
+	for (size_t i = 0; i < s.materials.size(); ++i) {
+		const rtbs_material& m = s.materials[i]; DevMaterial& d = out.materials[i];
+		d.kind = m.kind; d.tex = m.tex; d.param = m.param; d.pad = 0.0f;
+		d.albedo[0] = m.albedo[0]; d.albedo[1] = m.albedo[1]; d.albedo[2] = m.albedo[2]; d.albedo[3] = 0.0f;
+	}
+	out.textures.resize(s.textures.size());
+	for (size_t i = 0; i < s.textures.size(); ++i) {
+		const rtbs_texture& t = s.textures[i]; DevTexture& d = out.textures[i];
+		d.kind = t.kind; d.even = t.even; d.odd = t.odd;
+		d.scale = (t.kind == RTB_TEX_CHECKER) ? 1.0f / t.scale : t.scale;  // checker_texture ctor: inv_scale(1.0f/scale)
+		d.rgb[0] = t.rgb[0]; d.rgb[1] = t.rgb[1]; d.rgb[2] = t.rgb[2]; d.rgb[3] = 0.0f;
+		d.width = t.width; d.height = t.height; d.blob_offset = t.blob_offset; d.pad = 0;
+	}
+	out.blob = s.blob;
+	out.background_mode = s.background_mode;
+	memcpy(out.background, s.background, 12);
+	return RTB_OK;
+}
+
+}  // namespace rtb
+
+// ============================================================== cameras (cu_Cameras.cuh ctors restated, host arithmetic)
+
+namespace {
+struct H3 { float x, y, z; };
+H3 hsub(H3 a, H3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+H3 hmul(H3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+H3 hcross(H3 x, H3 y) { return {x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y}; }  // glm::cross
+H3 hnormalize(H3 v) { float d = v.x * v.x + v.y * v.y + v.z * v.z; return hmul(v, 1.0f / std::sqrt(d)); }   // glm::normalize
+void put3(float* d, H3 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
+H3 get3(const float* p) { return {p[0], p[1], p[2]}; }
+}  // namespace
+
+extern "C" {
+
+int rtb_camera_pinhole(rtb_camera* c, const float lf[3], const float la[3], const float up[3], float vfov, float aspect) {
+	int rc = rtb_camera_motion(c, lf, la, up, vfov, aspect, 0.0f, 0.0f);
+	if (rc) return rc;
+	c->kind = RTB_CAM_PINHOLE;
+	return RTB_OK;
+}
+int rtb_camera_motion(rtb_camera* c, const float lf[3], const float la[3], const float up[3], float vfov, float aspect, float t0, float t1) {
+	if (!c || !lf || !la || !up) return fail(RTB_ERR_INVALID, "rtb_camera_motion: null argument");
+	memset(c, 0, sizeof *c);
+	c->kind = RTB_CAM_MOTION; c->t0 = t0; c->t1 = t1;
+	float theta = vfov * 0.01745329251994329576923690768489f;
+	float vh = tanf(theta * 0.5f), vw = vh * aspect;
+	H3 w = hnormalize(hsub(get3(la), get3(lf)));
+	H3 u = hmul(hnormalize(hcross(get3(up), w)), vw);
+	H3 v = hmul(hnormalize(hcross(w, u)), vh);
+	put3(c->o, get3(lf)); put3(c->u, u); put3(c->v, v); put3(c->w, w);
+	c->viewport_width = vw; c->viewport_height = vh; c->focus_dist = 1.0f;
+	return RTB_OK;
+}
+int rtb_camera_defocus(rtb_camera* c, const float lf[3], const float la[3], const float up[3], float vfov, float aspect,
+                       float aperture, float focus_dist, float t0, float t1) {
+	if (!c || !lf || !la || !up) return fail(RTB_ERR_INVALID, "rtb_camera_defocus: null argument");
+	memset(c, 0, sizeof *c);
+	c->kind = RTB_CAM_DEFOCUS; c->t0 = t0; c->t1 = t1;
+	float theta = vfov * 0.01745329251994329576923690768489f;
+	c->viewport_height = tanf(theta * 0.5f); c->viewport_width = c->viewport_height * aspect;
+	H3 w = hnormalize(hsub(get3(la), get3(lf)));
+	H3 u = hnormalize(hcross(get3(up), w));
+	H3 v = hnormalize(hcross(w, u));
+	put3(c->o, get3(lf)); put3(c->u, u); put3(c->v, v); put3(c->w, w);
+	c->lens_radius = aperture * 0.5f; c->focus_dist = focus_dist;
+	return RTB_OK;
+}
+
+}  // extern "C"
