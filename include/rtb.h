@@ -199,6 +199,16 @@ int  rtb_download(rtb_renderer* r, float* host_rgba);
 /* Raw accumulators (rgb sums + count) and sums of squares; either pointer may be NULL. */
 int  rtb_download_accum(rtb_renderer* r, float* host_sum, float* host_sum2);
 int  rtb_get_counters(rtb_renderer* r, rtb_counters* out);
+
+/* Per-kernel-class device time, measured with CUDA events around every launch on the stream the
+ * kernels run on.  Profiling renders run as plain stream launches (no CUDA graph) and are meant for
+ * the roofline accounting of bench.py, not for the headline timing. */
+typedef struct rtb_profile {
+	double   generate_ms, traverse_ms, shade_ms, accumulate_ms;
+	uint64_t generate_launches, traverse_launches, shade_launches, accumulate_launches;
+} rtb_profile;
+int  rtb_renderer_set_profiling(rtb_renderer* r, int on);
+int  rtb_get_profile(rtb_renderer* r, rtb_profile* out);   /* synchronizes; totals since the last call */
 int  rtb_reset_counters(rtb_renderer* r);
 
 /* ------------------------------------------------------------------ hit-record parity hook */

@@ -1,0 +1,108 @@
+// oracle/ref_render_harness.cu — TEST INFRASTRUCTURE.  Drives the REFERENCE's own renderer — Renderer.cu,
+// BVH.cu, SphereHittable.cu, Scenes.cu, cuHostRND.cpp compiled unmodified for sm_100a from where they lie
+// under /root/reference — the way FirstApp::MakeApp / Run do (main/src/FirstApp.cpp:20-56,94-101), and dumps
+// what the parity tests need.  Needs a GPU.
+//
+//   ref_render render <w> <h> <spp> <depth> <out.bin>   raw w*h float4 framebuffer (post clamp+sqrt) + JSON timing
+//   ref_render scene <out.bin>                            the 488 spheres + raw material bytes SceneBook2BVH built
+//   ref_render rng <out.bin>                              cuHostRND(512,1984) stream and device XORWOW streams
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <cuda_runtime.h>
+#include <curand_kernel.h>
+#include <glm/glm.hpp>
+
+#include "Renderer.h"
+#include "rt_engine/geometry/BVH.cuh"
+#include "rt_engine/geometry/Scenes.h"
+#include "rt_engine/geometry/SphereHittable.cuh"
+#include "rt_engine/shaders/cu_Cameras.cuh"
+#include "utilities/cuda_utilities/cuHostRND.h"
+
+// Layout mirrors of classes whose members are private without accessors (Scenes.h:55-72,
+// SphereHittable.cuh:104-158); used by the harness only.
+struct SphereHandleView { aabb bounds; Material* material_ptr; Sphere* sphere_ptr; MovingSphere* moving_sphere_ptr; Hittable* hittable_ptr; };
+struct SceneView { BVH_Handle* bvh; aabb* world_bounds; std::vector<SphereHandle> sphere_handles; };
+static_assert(sizeof(SphereHandleView) == sizeof(SphereHandle), "SphereHandle layout");
+
+__global__ void xorwow_kernel(unsigned long long seed, int n, float* out) {
+	curandStateXORWOW_t st;
+	curand_init(seed, 0, 0, &st);
+	for (int i = 0; i < n; ++i) out[i] = curand_uniform(&st);
+}
+
+static int cmd_render(int argc, char** argv) {
+	if (argc != 7) return 2;
+	uint32_t w = atoi(argv[2]), h = atoi(argv[3]), spp = atoi(argv[4]), depth = atoi(argv[5]);
+	auto cam = new MotionBlurCamera(glm::vec3(13, 2, 3), glm::vec3(0, 0, 0), glm::vec3(0, 1, 0), 30.0f, w / (float)h, 0.1f, 1.0f);
+	SceneBook2BVH::Factory scene_factory{};
+	SceneBook2BVH* scene = scene_factory.MakeScene();
+	Renderer renderer = Renderer::MakeRenderer(w, h, spp, depth, cam, scene->getWorldPtr());
+	std::vector<glm::vec4> fb((size_t)w * h);
+	auto t0 = std::chrono::steady_clock::now();
+	renderer.Render();   // synchronous (Renderer.cu:132-133)
+	auto t1 = std::chrono::steady_clock::now();
+	renderer.DownloadRenderbuffer(fb.data());
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
+	FILE* o = fopen(argv[6], "wb"); if (!o) return 1;
+	fwrite(fb.data(), sizeof(glm::vec4), fb.size(), o); fclose(o);
+	double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+	printf("REF_JSON {\"width\": %u, \"height\": %u, \"spp\": %u, \"depth\": %u, \"render_ms\": %.3f, \"mpaths_per_s\": %.3f}\n", w, h, spp, depth, ms,
+	       (double)w * h * spp / ms * 1e-3);
+	return 0;
+}
+
+static int cmd_scene(int argc, char** argv) {
+	if (argc != 3) return 2;
+	SceneBook2BVH::Factory scene_factory{};
+	SceneBook2BVH* scene = scene_factory.MakeScene();
+	const SceneView* view = reinterpret_cast<const SceneView*>(scene);
+	FILE* o = fopen(argv[2], "wb"); if (!o) return 1;
+	int32_t n = (int32_t)view->sphere_handles.size();
+	fwrite(&n, 4, 1, o);
+	for (int i = 0; i < n; ++i) {
+		const SphereHandleView* hv = reinterpret_cast<const SphereHandleView*>(&view->sphere_handles[i]);
+		float rec[16]; memset(rec, 0, sizeof rec);   // [0] moving flag, [1..7] geometry, [8..13] raw material bytes 8..32
+		unsigned char mat[24];
+		cudaMemcpy(mat, hv->material_ptr, 24, cudaMemcpyDeviceToHost);
+		if (hv->moving_sphere_ptr) { rec[0] = 1.0f; cudaMemcpy(rec + 1, hv->moving_sphere_ptr, sizeof(MovingSphere), cudaMemcpyDeviceToHost); }
+		else cudaMemcpy(rec + 1, hv->sphere_ptr, sizeof(Sphere), cudaMemcpyDeviceToHost);
+		memcpy(rec + 8, mat + 8, 16);
+		fwrite(rec, 4, 16, o);
+	}
+	fclose(o);
+	return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+static int cmd_rng(int argc, char** argv) {
+	if (argc != 3) return 2;
+	FILE* o = fopen(argv[2], "wb"); if (!o) return 1;
+	{   // the reference's scene-construction stream (device generator behind the cuRAND host API)
+		cuHostRND rnd(512, 1984);
+		std::vector<float> u(4608);
+		for (auto& x : u) x = rnd.next();
+		fwrite(u.data(), 4, u.size(), o);
+	}
+	const unsigned long long seeds[4] = {1984ull, 1985ull, 1984ull + 45000ull, 1984ull + 89999ull};
+	float* d; cudaMalloc(&d, 64 * 4);
+	for (int s = 0; s < 4; ++s) {
+		xorwow_kernel<<<1, 1>>>(seeds[s], 64, d);
+		float hbuf[64]; cudaMemcpy(hbuf, d, sizeof hbuf, cudaMemcpyDeviceToHost);
+		fwrite(hbuf, 4, 64, o);
+	}
+	fclose(o);
+	return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int main(int argc, char** argv) {
+	if (argc < 2) { fprintf(stderr, "usage: ref_render render|scene|rng ...\n"); return 2; }
+	if (!strcmp(argv[1], "render")) return cmd_render(argc, argv);
+	if (!strcmp(argv[1], "scene")) return cmd_scene(argc, argv);
+	if (!strcmp(argv[1], "rng")) return cmd_rng(argc, argv);
+	return 2;
+}

@@ -61,6 +61,11 @@ class Counters(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("launches", C.c_uint64), ("batches", C.c_uint64), ("render_ms", C.c_double)]
 
 
+class Profile(C.Structure):
+    _fields_ = [("generate_ms", C.c_double), ("traverse_ms", C.c_double), ("shade_ms", C.c_double), ("accumulate_ms", C.c_double),
+                ("generate_launches", C.c_uint64), ("traverse_launches", C.c_uint64), ("shade_launches", C.c_uint64), ("accumulate_launches", C.c_uint64)]
+
+
 class SceneInfo(C.Structure):
     _fields_ = [("camera", Camera), ("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("max_depth", C.c_int32)]
 
@@ -123,6 +128,8 @@ ABI = {
     "rtb_download_accum": (C.c_int, [_P, _P, _P]),
     "rtb_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "rtb_reset_counters": (C.c_int, [_P]),
+    "rtb_renderer_set_profiling": (C.c_int, [_P, C.c_int]),
+    "rtb_get_profile": (C.c_int, [_P, C.POINTER(Profile)]),
     "rtb_trace_rays": (C.c_int, [_P, _P, C.c_size_t, _P]),
 }
 SCENES_ABI = {
@@ -342,6 +349,14 @@ class Renderer:
         c = Counters()
         _check(lib().rtb_get_counters(self.handle, C.byref(c)), "rtb_get_counters")
         return c
+
+    def set_profiling(self, on: bool):
+        _check(lib().rtb_renderer_set_profiling(self.handle, 1 if on else 0), "rtb_renderer_set_profiling")
+
+    def profile(self) -> Profile:
+        p = Profile()
+        _check(lib().rtb_get_profile(self.handle, C.byref(p)), "rtb_get_profile")
+        return p
 
     def reset_counters(self):
         _check(lib().rtb_reset_counters(self.handle), "rtb_reset_counters")

@@ -53,7 +53,28 @@ struct rtb_renderer {
 	float4 *graph_accum = nullptr;
 
 	uint64_t launches = 0, batches = 0;
+
+	// optional per-launch event timing (rtb_renderer_set_profiling)
+	bool profiling = false;
+	std::vector<cudaEvent_t> prof_events;      // pairs (begin, end)
+	std::vector<int> prof_class;               // 0 generate, 1 traverse, 2 shade, 3 accumulate
+	size_t prof_used = 0;
 };
+
+static void prof_begin(rtb_renderer* r, int cls, cudaStream_t st) {
+	if (!r->profiling) return;
+	if (r->prof_used == r->prof_class.size()) {
+		cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+		r->prof_events.push_back(a); r->prof_events.push_back(b); r->prof_class.push_back(cls);
+	}
+	r->prof_class[r->prof_used] = cls;
+	cudaEventRecord(r->prof_events[2 * r->prof_used], st);
+}
+static void prof_end(rtb_renderer* r, cudaStream_t st) {
+	if (!r->profiling) return;
+	cudaEventRecord(r->prof_events[2 * r->prof_used + 1], st);
+	r->prof_used++;
+}
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -98,6 +119,7 @@ void rtb_renderer_destroy(rtb_renderer* r) {
 	cudaSetDevice(r->device);
 	cudaStreamSynchronize(r->stream);
 	free_graph(r);
+	for (cudaEvent_t e : r->prof_events) cudaEventDestroy(e);
 	cudaFree(r->d_scene); cudaFree(r->d_accum); cudaFree(r->d_accum2); cudaFree(r->d_out); cudaFree(r->d_wave);
 	cudaEventDestroy(r->ev_in); cudaEventDestroy(r->ev_out); cudaEventDestroy(r->ev_t0); cudaEventDestroy(r->ev_t1);
 	cudaStreamDestroy(r->stream);
@@ -198,12 +220,12 @@ static int ensure_wave(rtb_renderer* r, size_t paths, uint32_t depth) {
 }
 
 static void enqueue_batch(rtb_renderer* r, const BatchParams& bp, cudaStream_t st) {
-	launch_generate(bp, r->cam, r->wv, r->lc, st);
+	prof_begin(r, 0, st); launch_generate(bp, r->cam, r->wv, r->lc, st); prof_end(r, st);
 	for (uint32_t b = 0; b < bp.max_depth; ++b) {
-		launch_traverse(r->sv, bp, r->wv, b, r->lc, st);
-		launch_shade(r->sv, bp, r->wv, b, r->lc, st);
+		prof_begin(r, 1, st); launch_traverse(r->sv, bp, r->wv, b, r->lc, st); prof_end(r, st);
+		prof_begin(r, 2, st); launch_shade(r->sv, bp, r->wv, b, r->lc, st); prof_end(r, st);
 	}
-	launch_accumulate(bp, r->wv, r->d_accum, r->d_accum2, r->lc, st);
+	prof_begin(r, 3, st); launch_accumulate(bp, r->wv, r->d_accum, r->d_accum2, r->lc, st); prof_end(r, st);
 }
 
 int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
@@ -252,7 +274,7 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 
 	const uint32_t n_batches = spp ? (uint32_t)((spp + S - 1) / S) : 0;
 	const uint64_t launches_per_batch = 3 + 2ull * bp.max_depth;
-	const bool use_graph = getenv("RTB_NO_GRAPH") == nullptr && n_batches > 0;
+	const bool use_graph = getenv("RTB_NO_GRAPH") == nullptr && n_batches > 0 && !r->profiling;
 	if (use_graph) {
 		bool reuse = r->graph_valid && memcmp(&r->graph_bp, &bp, sizeof bp) == 0 && memcmp(&r->graph_cam, &r->cam, sizeof r->cam) == 0 &&
 		             r->graph_scene_version == r->scene_version && r->graph_accum == r->d_accum;
@@ -339,6 +361,32 @@ int rtb_get_counters(rtb_renderer* r, rtb_counters* out) {
 	}
 	out->launches = r->launches; out->batches = r->batches;
 	if (r->timed) { float ms = 0.0f; if (cudaEventElapsedTime(&ms, r->ev_t0, r->ev_t1) == cudaSuccess) out->render_ms = ms; else cudaGetLastError(); }
+	return RTB_OK;
+}
+
+int rtb_renderer_set_profiling(rtb_renderer* r, int on) {
+	if (!r) return fail(RTB_ERR_INVALID, "rtb_renderer_set_profiling: null renderer");
+	CUDA_TRY(cudaSetDevice(r->device));
+	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	r->profiling = on != 0;
+	r->prof_used = 0;
+	return RTB_OK;
+}
+
+int rtb_get_profile(rtb_renderer* r, rtb_profile* out) {
+	if (!r || !out) return fail(RTB_ERR_INVALID, "rtb_get_profile: null argument");
+	memset(out, 0, sizeof *out);
+	CUDA_TRY(cudaSetDevice(r->device));
+	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	double ms[4] = {0, 0, 0, 0}; uint64_t cnt[4] = {0, 0, 0, 0};
+	for (size_t i = 0; i < r->prof_used; ++i) {
+		float t = 0.0f;
+		CUDA_TRY(cudaEventElapsedTime(&t, r->prof_events[2 * i], r->prof_events[2 * i + 1]));
+		ms[r->prof_class[i]] += t; cnt[r->prof_class[i]]++;
+	}
+	out->generate_ms = ms[0]; out->traverse_ms = ms[1]; out->shade_ms = ms[2]; out->accumulate_ms = ms[3];
+	out->generate_launches = cnt[0]; out->traverse_launches = cnt[1]; out->shade_launches = cnt[2]; out->accumulate_launches = 2 * cnt[3];
+	r->prof_used = 0;
 	return RTB_OK;
 }
 
