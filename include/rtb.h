@@ -133,6 +133,11 @@ int rtb_bvh_build(const float* aabbs, int n, int builder, rtb_bvh_node* nodes_ou
  * (leaf payload = flattened primitive index).  Pass NULL to query the node count. */
 int rtb_scene_world_bvh(const rtb_scene* s, rtb_bvh_node* nodes_out, int cap, int* root_out);
 
+/* Host-only: runs the flattener (instances -> record slots, world BVH) without touching the GPU and
+ * reports its sizes; also fills the world BVH returned by rtb_scene_world_bvh.  out4 = {primitives
+ * (BVH leaves), 64-byte record slots, inner nodes of the wide layout, tree depth}. */
+int rtb_scene_flatten_stats(rtb_scene* s, int32_t out4[4]);
+
 /* ------------------------------------------------------------------ cameras */
 
 enum rtb_camera_kind { RTB_CAM_PINHOLE = 0, RTB_CAM_DEFOCUS = 1, RTB_CAM_MOTION = 2 };
@@ -185,6 +190,8 @@ void rtb_renderer_destroy(rtb_renderer* r);
 /* Flattens the scene graph into SoA device buffers + one world BVH and uploads them. */
 int  rtb_renderer_set_scene(rtb_renderer* r, rtb_scene* s);
 int  rtb_renderer_set_camera(rtb_renderer* r, const rtb_camera* cam);
+/* Bytes of the scene arena rtb_renderer_set_scene copies host -> device. */
+size_t rtb_renderer_scene_bytes(const rtb_renderer* r);
 /* Renders asynchronously on `stream`, ADDING radiance sums into the accumulators. */
 int  rtb_render(rtb_renderer* r, const rtb_render_params* p, void* stream);
 int  rtb_synchronize(rtb_renderer* r);
@@ -206,6 +213,8 @@ int  rtb_get_counters(rtb_renderer* r, rtb_counters* out);
 typedef struct rtb_profile {
 	double   generate_ms, traverse_ms, shade_ms, accumulate_ms;
 	uint64_t generate_launches, traverse_launches, shade_launches, accumulate_launches;
+	double   tail_ms;          /* fused traverse+shade kernel that finishes short queues */
+	uint64_t tail_launches;
 } rtb_profile;
 int  rtb_renderer_set_profiling(rtb_renderer* r, int on);
 int  rtb_get_profile(rtb_renderer* r, rtb_profile* out);   /* synchronizes; totals since the last call */

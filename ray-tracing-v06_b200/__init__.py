@@ -63,7 +63,8 @@ class Counters(C.Structure):
 
 class Profile(C.Structure):
     _fields_ = [("generate_ms", C.c_double), ("traverse_ms", C.c_double), ("shade_ms", C.c_double), ("accumulate_ms", C.c_double),
-                ("generate_launches", C.c_uint64), ("traverse_launches", C.c_uint64), ("shade_launches", C.c_uint64), ("accumulate_launches", C.c_uint64)]
+                ("generate_launches", C.c_uint64), ("traverse_launches", C.c_uint64), ("shade_launches", C.c_uint64), ("accumulate_launches", C.c_uint64),
+                ("tail_ms", C.c_double), ("tail_launches", C.c_uint64)]
 
 
 class SceneInfo(C.Structure):
@@ -111,6 +112,7 @@ ABI = {
     "rtb_scene_serialize": (C.c_size_t, [_P, _P, C.c_size_t]),
     "rtb_bvh_build": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_int)]),
     "rtb_scene_world_bvh": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int)]),
+    "rtb_scene_flatten_stats": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "rtb_camera_pinhole": (C.c_int, [C.POINTER(Camera), _F3, _F3, _F3, C.c_float, C.c_float]),
     "rtb_camera_defocus": (C.c_int, [C.POINTER(Camera), _F3, _F3, _F3, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
     "rtb_camera_motion": (C.c_int, [C.POINTER(Camera), _F3, _F3, _F3, C.c_float, C.c_float, C.c_float, C.c_float]),
@@ -119,6 +121,7 @@ ABI = {
     "rtb_renderer_destroy": (None, [_P]),
     "rtb_renderer_set_scene": (C.c_int, [_P, _P]),
     "rtb_renderer_set_camera": (C.c_int, [_P, C.POINTER(Camera)]),
+    "rtb_renderer_scene_bytes": (C.c_size_t, [_P]),
     "rtb_render": (C.c_int, [_P, C.POINTER(RenderParams), _P]),
     "rtb_synchronize": (C.c_int, [_P]),
     "rtb_renderer_accum_ptr": (_P, [_P]),
@@ -284,6 +287,11 @@ class Scene:
         lib().rtb_scene_serialize(self.handle, buf, n)
         return buf.raw
 
+    def flatten_stats(self) -> dict:
+        out = (C.c_int32 * 4)()
+        _check(lib().rtb_scene_flatten_stats(self.handle, out), "rtb_scene_flatten_stats")
+        return {"primitives": out[0], "record_slots": out[1], "inner_nodes": out[2], "depth": out[3]}
+
     def world_bvh(self):
         root = C.c_int(-1)
         n = _check(lib().rtb_scene_world_bvh(self.handle, None, 0, C.byref(root)), "rtb_scene_world_bvh")
@@ -311,6 +319,9 @@ class Renderer:
     def set_scene(self, scene: Scene):
         _check(lib().rtb_renderer_set_scene(self.handle, scene.handle), "rtb_renderer_set_scene")
         self._scene = scene
+
+    def scene_bytes(self) -> int:
+        return int(lib().rtb_renderer_scene_bytes(self.handle))
 
     def set_camera(self, cam: Camera):
         _check(lib().rtb_renderer_set_camera(self.handle, C.byref(cam)), "rtb_renderer_set_camera")

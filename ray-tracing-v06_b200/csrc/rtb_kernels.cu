@@ -67,6 +67,7 @@ generate_kernel(BatchParams bp, rtb_camera cam, WaveView wv) {
 	if (blockIdx.x == 0) {
 		for (uint32_t i = threadIdx.x; i <= bp.max_depth; i += blockDim.x) wv.n_live[i] = (i == 0) ? n : 0u;
 		for (uint32_t i = threadIdx.x; i < 2 * (bp.max_depth + 1); i += blockDim.x) wv.work[i] = 0u;
+		if (threadIdx.x == 0) *wv.tail_from = 0xFFFFFFFFu;
 	}
 
 	const float px = 1.0f / (float)bp.width, py = 1.0f / (float)bp.height;   // pixel_size  Renderer.cu:188
@@ -186,15 +187,83 @@ __device__ __forceinline__ float medium_box_hit(v3 o, v3 d, float a, float4 q0, 
 	return medium_sample(tn, tf, a, q2.w, u, tbest);
 }
 
+// Instances.  T = (cos, sin, off.x, off.y), (off.z, -, -, -) with world = R_y(theta) * object + off.
+__device__ __forceinline__ int xf_offset(int base) { return base == PRIM_SPHERE ? 1 : (base == PRIM_MOVING_SPHERE ? 2 : 4); }
+
+// world ray -> object ray: origin - offset (book translate::hit), then rotate by -theta (book rotate_y::hit)
+__device__ __forceinline__ void xf_ray(const float4* tp, v3 o, v3 d, v3& oo, v3& dd) {
+	const float4 t0 = ldg4(tp), t1 = ldg4(tp + 1);
+	const float cs = t0.x, sn = t0.y;
+	const v3 ot = rt::sub(o, rt::mk(t0.z, t0.w, t1.x));
+	oo = rt::mk(fmaf(cs, ot.x, -(sn * ot.z)), ot.y, fmaf(sn, ot.x, cs * ot.z));
+	dd = rt::mk(fmaf(cs, d.x, -(sn * d.z)), d.y, fmaf(sn, d.x, cs * d.z));
+}
+// object vector -> world (book rotate_y::hit, normal back-rotation)
+__device__ __forceinline__ v3 xf_vec_to_world(const float4* tp, v3 v) {
+	const float4 t0 = ldg4(tp);
+	const float cs = t0.x, sn = t0.y;
+	return rt::mk(fmaf(cs, v.x, sn * v.z), v.y, fmaf(-sn, v.x, cs * v.z));
+}
+
 // ------------------------------------------------------------------------------------------------
 // traverse
 
 struct MediumRng { uint32_t seed, pixel, sample, bounce; };
 
+// One primitive against one ray: the t of the hit if it is closer than tbest, else FLT_MAX.
+template <bool MEDIA>
+__device__ __forceinline__ float leaf_test(const SceneView& sv, int code, v3 o, v3 d, float a, float time, const MediumRng& mr, float tbest) {
+	const int type = code & 15;
+	const float4* pp = sv.prims + 4 * (size_t)(code >> RTB_LEAF_TYPE_BITS);
+	const float4 q0 = ldg4(pp);
+	float t = FLT_MAX;
+	if (type == PRIM_SPHERE) {
+		t = sphere_closest(o, d, a, xyz(q0), q0.w);
+	} else if (type == PRIM_MOVING_SPHERE) {
+		// center = mix(center0, center1, ray.time)   SphereHittable.cu:92
+		const float4 q1 = ldg4(pp + 1);
+		t = sphere_closest(o, d, a, rt::mix(xyz(q0), xyz(q1), time), q0.w);
+	} else if (type == PRIM_QUAD || type == PRIM_TRIANGLE) {
+		t = planar_hit(o, d, pp, q0, type == PRIM_TRIANGLE, tbest);
+	} else if (type & PRIM_XF) {
+		// instance: take the ray into the primitive's frame (book translate::hit, rotate_y::hit)
+		const int base = type & 7;
+		v3 oo, dd;
+		xf_ray(pp + xf_offset(base), o, d, oo, dd);
+		const float a2 = rt::dot(dd, dd);
+		if (base == PRIM_SPHERE) t = sphere_closest(oo, dd, a2, xyz(q0), q0.w);
+		else if (base == PRIM_MOVING_SPHERE) t = sphere_closest(oo, dd, a2, rt::mix(xyz(q0), xyz(ldg4(pp + 1)), time), q0.w);
+		else t = planar_hit(oo, dd, pp, q0, base == PRIM_TRIANGLE, tbest);
+	} else if (MEDIA) {
+		const float4 q1 = ldg4(pp + 1);
+		if (type == PRIM_MEDIUM_SPHERE) {
+			uint32_t mi = __float_as_uint(q1.y);
+			float u = rt::rng4(mr.seed, mr.pixel, mr.sample, mr.bounce, rt::STREAM_MEDIUM0 + mi).x;
+			t = medium_sphere_hit(o, d, a, q0, q1.x, u, tbest);
+		} else {
+			const float4 q2 = ldg4(pp + 2), q3 = ldg4(pp + 3);
+			uint32_t mi = __float_as_uint(q3.x);
+			float u = rt::rng4(mr.seed, mr.pixel, mr.sample, mr.bounce, rt::STREAM_MEDIUM0 + mi).x;
+			t = medium_box_hit(o, d, a, q0, q1, q2, u, tbest);
+		}
+	}
+	return t;
+}
+
 template <bool MEDIA>
 __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float time, const MediumRng& mr,
                                           int* __restrict__ stack, float& tbest_out, int& code_out) {
 	const float a = rt::dot(d, d);
+	float tbest = FLT_MAX;
+	int best = -1;
+	if (MEDIA) {   // media first: a scatter inside a medium bounds the BVH walk tightly
+		for (int k = 0; k < sv.n_pre; ++k) {
+			const int code = __ldg(sv.pre_list + k);
+			const float t = leaf_test<true>(sv, code, o, d, a, time, mr, tbest);
+			if (t < tbest) { tbest = t; best = code; }
+		}
+		if (sv.bvh_empty) { tbest_out = tbest; code_out = best; return; }
+	}
 	// Slab test with a per-ray reciprocal; an exactly-zero component is nudged so 0 * inf never appears.
 	const float gx = fabsf(d.x) < 1e-20f ? copysignf(1e-20f, d.x) : d.x;
 	const float gy = fabsf(d.y) < 1e-20f ? copysignf(1e-20f, d.y) : d.y;
@@ -202,8 +271,6 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 	const float idx = 1.0f / gx, idy = 1.0f / gy, idz = 1.0f / gz;
 	const float oix = -(o.x * idx), oiy = -(o.y * idy), oiz = -(o.z * idz);
 
-	float tbest = FLT_MAX;
-	int best = -1;
 	int cur = sv.root_ref;
 	int sp = 0;
 	for (;;) {
@@ -225,8 +292,10 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 			bool hl = ltmin <= ltmax && ltmin < tbest && ltmax > 0.0f;
 			bool hr = rtmin <= rtmax && rtmin < tbest && rtmax > 0.0f;
 			if (hl && hr) {
-				// nearer child next, farther child on the stack   BVH.cu:91-97
-				bool sw = ltmin > rtmin;
+				// nearer child next, farther child on the stack (BVH.cu:91-97); boxes that both contain
+				// the origin are ordered by where the ray leaves them
+				const float lk = fmaxf(ltmin, 0.0f), rk = fmaxf(rtmin, 0.0f);
+				bool sw = lk > rk || (lk == rk && ltmax > rtmax);
 				int nearc = sw ? n3.y : n3.x, farc = sw ? n3.x : n3.y;
 				stack[sp * TRAVERSE_THREADS] = farc; ++sp;
 				cur = nearc;
@@ -236,31 +305,7 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 			if (hr) { cur = n3.y; continue; }
 		} else {
 			const int code = ~cur;
-			const int type = code & 7;
-			const float4* pp = sv.prims + 4 * (size_t)(code >> 3);
-			const float4 q0 = ldg4(pp);
-			float t = FLT_MAX;
-			if (type == PRIM_SPHERE) {
-				t = sphere_closest(o, d, a, xyz(q0), q0.w);
-			} else if (type == PRIM_MOVING_SPHERE) {
-				// center = mix(center0, center1, ray.time)   SphereHittable.cu:92
-				const float4 q1 = ldg4(pp + 1);
-				t = sphere_closest(o, d, a, rt::mix(xyz(q0), xyz(q1), time), q0.w);
-			} else if (type == PRIM_QUAD || type == PRIM_TRIANGLE) {
-				t = planar_hit(o, d, pp, q0, type == PRIM_TRIANGLE, tbest);
-			} else if (MEDIA) {
-				const float4 q1 = ldg4(pp + 1);
-				if (type == PRIM_MEDIUM_SPHERE) {
-					uint32_t mi = __float_as_uint(q1.y);
-					float u = rt::rng4(mr.seed, mr.pixel, mr.sample, mr.bounce, rt::STREAM_MEDIUM0 + mi).x;
-					t = medium_sphere_hit(o, d, a, q0, q1.x, u, tbest);
-				} else {
-					const float4 q2 = ldg4(pp + 2), q3 = ldg4(pp + 3);
-					uint32_t mi = __float_as_uint(q3.x);
-					float u = rt::rng4(mr.seed, mr.pixel, mr.sample, mr.bounce, rt::STREAM_MEDIUM0 + mi).x;
-					t = medium_box_hit(o, d, a, q0, q1, q2, u, tbest);
-				}
-			}
+			const float t = leaf_test<MEDIA>(sv, code, o, d, a, time, mr, tbest);
 			if (t < tbest) { tbest = t; best = code; }   // "if (t >= rec.distance) return false"  SphereHittable.cu:58
 		}
 		if (sp == 0) break;
@@ -273,21 +318,23 @@ template <bool MEDIA>
 __global__ void __launch_bounds__(TRAVERSE_THREADS)
 traverse_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
 	__shared__ int s_stack[STACK_SIZE * TRAVERSE_THREADS];
+	if (bounce >= *wv.tail_from) return;
 	const uint32_t n = wv.n_live[bounce];
 	if (n == 0) return;
 	const uint32_t batch = *wv.batch_index;
 	const int lane = threadIdx.x & 31;
-	const float4* __restrict__ ro = wv.ray_o[bounce & 1];
-	const float4* __restrict__ rd = wv.ray_d[bounce & 1];
+	const float4* __restrict__ ro = (bounce & 1) ? wv.ray_o[1] : wv.ray_o[0];
+	const float4* __restrict__ rd = (bounce & 1) ? wv.ray_d[1] : wv.ray_d[0];
 	uint32_t* counter = wv.work + 2 * bounce;
-	for (;;) {
-		uint32_t base = 0;
-		if (lane == 0) base = atomicAdd(counter, 32u);
-		base = __shfl_sync(FULL_MASK, base, 0);
-		if (base >= n) break;
-		uint32_t i = base + lane;
+	// Every warp owns one static chunk of 32 rays; only when the queue is longer than the whole
+	// grid do warps pull further chunks from the device counter (short queues cost no atomics).
+	const uint32_t warps_total = gridDim.x * (TRAVERSE_THREADS / 32);
+	uint32_t base = (blockIdx.x * (TRAVERSE_THREADS / 32) + (threadIdx.x >> 5)) * 32u;
+	const uint32_t static_span = warps_total * 32u;
+	while (base < n) {
+		const uint32_t i = base + lane;
 		if (i < n) {
-			float4 fo = ro[i], fd = rd[i];
+			const float4 fo = ro[i], fd = rd[i];
 			MediumRng mr{0, 0, 0, 0};
 			if (MEDIA) {
 				mr.seed = bp.seed; mr.bounce = bounce;
@@ -298,6 +345,10 @@ traverse_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
 			wv.hit[i] = make_int2(__float_as_int(t), code);
 		}
 		__syncwarp();
+		if (n <= static_span) break;
+		uint32_t nb = 0;
+		if (lane == 0) nb = atomicAdd(counter, 32u);
+		base = static_span + __shfl_sync(FULL_MASK, nb, 0);
 	}
 }
 
@@ -309,37 +360,43 @@ struct Surface { v3 p, n_shade, n_geom; float u, v; };
 // What Sphere::getNormal / MovingSphere::getNormal hand to materials: the outward normal
 // (p - c) / r, never flipped (SphereHittable.cu:43-50,64,100).  Quads face the ray (book).
 __device__ __forceinline__ void reconstruct(const SceneView& sv, int code, v3 o, v3 d, float time, float t, bool want_uv, Surface& s) {
-	const int type = code & 7;
-	const float4* pp = sv.prims + 4 * (size_t)(code >> 3);
+	const int type = code & 15, base = type & 7;
+	const bool xf = (type & PRIM_XF) != 0;
+	const float4* pp = sv.prims + 4 * (size_t)(code >> RTB_LEAF_TYPE_BITS);
 	const float4 q0 = ldg4(pp);
-	s.p = rt::madd(d, t, o);
+	s.p = rt::madd(d, t, o);          // Material::Scatter uses in_ray.at(rec.distance): the world ray
 	s.u = 0.0f; s.v = 0.0f;
-	if (type == PRIM_SPHERE || type == PRIM_MOVING_SPHERE) {
-		v3 c = xyz(q0);
-		if (type == PRIM_MOVING_SPHERE) c = rt::mix(c, xyz(ldg4(pp + 1)), time);
-		s.n_geom = rt::divs(rt::sub(s.p, c), q0.w);
+	if (type == PRIM_MEDIUM_SPHERE || type == PRIM_MEDIUM_BOX) {   // normal arbitrary (book constant_medium::hit)
+		s.n_geom = rt::mk(1.0f, 0.0f, 0.0f);
 		s.n_shade = s.n_geom;
-		if (want_uv) {   // book sphere::get_sphere_uv, on the normal taken back to the sphere's own frame
-			const float4 qr = ldg4(pp + (type == PRIM_MOVING_SPHERE ? 2 : 1));
-			const float nx = fmaf(qr.x, s.n_geom.x, -(qr.y * s.n_geom.z)), nz = fmaf(qr.y, s.n_geom.x, qr.x * s.n_geom.z);
-			float theta = acosf(-s.n_geom.y);
-			float phi = atan2f(-nz, nx) + 3.14159265358979323846f;
+		return;
+	}
+	v3 oo = o, dd = d;                // the ray in the primitive's own frame
+	const float4* tp = pp + xf_offset(base);
+	if (xf) xf_ray(tp, o, d, oo, dd);
+	if (base == PRIM_SPHERE || base == PRIM_MOVING_SPHERE) {
+		v3 c = xyz(q0);
+		if (base == PRIM_MOVING_SPHERE) c = rt::mix(c, xyz(ldg4(pp + 1)), time);
+		v3 n = rt::divs(rt::sub(rt::madd(dd, t, oo), c), q0.w);   // (ray.at(t) - center) / radius   SphereHittable.cu:64,100
+		if (want_uv) {   // book sphere::get_sphere_uv on the outward normal in the sphere's own frame
+			float theta = acosf(-n.y);
+			float phi = atan2f(-n.z, n.x) + 3.14159265358979323846f;
 			s.u = phi / 6.28318530717958647692f;
 			s.v = theta / 3.14159265358979323846f;
 		}
-	} else if (type == PRIM_QUAD || type == PRIM_TRIANGLE) {
+		if (xf) n = xf_vec_to_world(tp, n);
+		s.n_geom = n; s.n_shade = n;
+	} else {
 		const float4 q1 = ldg4(pp + 1), q2 = ldg4(pp + 2), q3 = ldg4(pp + 3);
 		v3 N = rt::mk(q1.w, q2.w, q3.w);
-		s.n_geom = N;
-		s.n_shade = rt::dot(d, N) > 0.0f ? rt::neg(N) : N;
+		v3 ns = rt::dot(dd, N) > 0.0f ? rt::neg(N) : N;             // book set_face_normal
 		if (want_uv) {
-			v3 planar = rt::sub(s.p, xyz(q0));
+			v3 planar = rt::sub(rt::madd(dd, t, oo), xyz(q0));
 			s.u = rt::dot(xyz(q3), rt::cross(planar, xyz(q2)));
 			s.v = rt::dot(xyz(q3), rt::cross(xyz(q1), planar));
 		}
-	} else {  // medium: normal arbitrary (book constant_medium::hit)
-		s.n_geom = rt::mk(1.0f, 0.0f, 0.0f);
-		s.n_shade = s.n_geom;
+		if (xf) { N = xf_vec_to_world(tp, N); ns = xf_vec_to_world(tp, ns); }
+		s.n_geom = N; s.n_shade = ns;
 	}
 }
 
@@ -477,57 +534,71 @@ __device__ __forceinline__ v3 background(const SceneView& sv, v3 d) {
 // ------------------------------------------------------------------------------------------------
 // shade: one path segment of sample_world (Renderer.cu:146-176) + block-level queue compaction
 
+// Shades one traversed segment.  Returns true when the path continues (no/nd/nthr hold the scattered
+// ray and the updated throughput); otherwise the path has ended and its contribution (if any) has
+// been written to contrib[path].
+__device__ __forceinline__ bool shade_segment(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t batch, uint32_t bounce,
+                                              const float4& fo, const float4& fd, v3 thr, float t, int code,
+                                              float4& no, float4& nd, v3& nthr) {
+	const uint32_t path = __float_as_uint(fd.w);
+	const v3 o = xyz(fo), d = xyz(fd);
+	if (code < 0) {
+		v3 c = rt::mulv(thr, background(sv, d));          // miss: throughput * sky   Renderer.cu:153
+		wv.contrib[path] = make_float4(c.x, c.y, c.z, 0.0f);
+		return false;
+	}
+	const int2 info = __ldg(sv.prim_info + (code >> RTB_LEAF_TYPE_BITS));
+	const int tex = __float_as_int(ldg4(sv.materials + 2 * info.x).y);
+	Surface s;
+	reconstruct(sv, code, o, d, fo.w, t, texture_needs_uv(sv, tex), s);
+	uint32_t pixel, sample;
+	path_pixel_sample(bp, batch, path, pixel, sample);
+	const rt::f4 r = rt::rng4(bp.seed, pixel, sample, bounce, rt::STREAM_SCATTER);
+	v3 dir, att;
+	const int res = scatter(sv, info.x, s, d, r, dir, att);
+	if (res == 2) {                                       // emitter: throughput * emitted, path ends
+		v3 c = rt::mulv(thr, att);
+		wv.contrib[path] = make_float4(c.x, c.y, c.z, 0.0f);
+		return false;
+	}
+	if (res != 1 || bounce + 1 >= bp.max_depth) return false;   // absorbed, or out of depth: black   Renderer.cu:164,180
+	// scatter_ray = Ray(at(t), dir, time); o += d * 0.001   Renderer.cu:168-175
+	v3 o2 = rt::madd(dir, 0.001f, s.p);
+	nthr = rt::mulv(thr, att);
+	no = make_float4(o2.x, o2.y, o2.z, fo.w);
+	nd = make_float4(dir.x, dir.y, dir.z, fd.w);
+	return true;
+}
+
 __global__ void __launch_bounds__(SHADE_THREADS)
 shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
 	__shared__ uint32_t s_chunk, s_base;
 	__shared__ uint32_t s_warp[SHADE_THREADS / 32];
+	if (bounce >= *wv.tail_from) return;
 	const uint32_t n = wv.n_live[bounce];
 	if (n == 0) return;
 	const uint32_t batch = *wv.batch_index;
 	const int in = bounce & 1, out = in ^ 1;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const bool last = bounce + 1 >= bp.max_depth;
+	const float4* __restrict__ ro = in ? wv.ray_o[1] : wv.ray_o[0];
+	const float4* __restrict__ rd = in ? wv.ray_d[1] : wv.ray_d[0];
+	const float4* __restrict__ rt_ = in ? wv.thr[1] : wv.thr[0];
+	float4* __restrict__ wo = out ? wv.ray_o[1] : wv.ray_o[0];
+	float4* __restrict__ wd = out ? wv.ray_d[1] : wv.ray_d[0];
+	float4* __restrict__ wt = out ? wv.thr[1] : wv.thr[0];
 	uint32_t* counter = wv.work + 2 * bounce + 1;
+	// the first chunk of every block is static; further chunks come from the device counter
+	uint32_t base = blockIdx.x * SHADE_THREADS;
+	const uint32_t static_span = gridDim.x * SHADE_THREADS;
 	for (;;) {
-		if (threadIdx.x == 0) s_chunk = atomicAdd(counter, (uint32_t)SHADE_THREADS);
-		__syncthreads();
-		const uint32_t base = s_chunk;
 		if (base >= n) break;
 		const uint32_t i = base + threadIdx.x;
 		bool alive = false;
-		float4 no = make_float4(0, 0, 0, 0), nd = no, nt = no;
+		float4 no = make_float4(0, 0, 0, 0), nd = no; v3 nthr = rt::mk(0, 0, 0);
 		if (i < n) {
-			const float4 fo = wv.ray_o[in][i], fd = wv.ray_d[in][i], ft = wv.thr[in][i];
+			const float4 fo = ro[i], fd = rd[i], ft = rt_[i];
 			const int2 h = wv.hit[i];
-			const uint32_t path = __float_as_uint(fd.w);
-			const v3 o = xyz(fo), d = xyz(fd), thr = xyz(ft);
-			if (h.y < 0) {
-				v3 c = rt::mulv(thr, background(sv, d));          // miss: throughput * sky   Renderer.cu:153
-				wv.contrib[path] = make_float4(c.x, c.y, c.z, 0.0f);
-			} else {
-				const float t = __int_as_float(h.x);
-				const int2 info = __ldg(sv.prim_info + (h.y >> 3));
-				const int tex = __float_as_int(ldg4(sv.materials + 2 * info.x).y);
-				Surface s;
-				reconstruct(sv, h.y, o, d, fo.w, t, texture_needs_uv(sv, tex), s);
-				uint32_t pixel, sample;
-				path_pixel_sample(bp, batch, path, pixel, sample);
-				const rt::f4 r = rt::rng4(bp.seed, pixel, sample, bounce, rt::STREAM_SCATTER);
-				v3 dir, att;
-				const int res = scatter(sv, info.x, s, d, r, dir, att);
-				if (res == 2) {
-					v3 c = rt::mulv(thr, att);
-					wv.contrib[path] = make_float4(c.x, c.y, c.z, 0.0f);
-				} else if (res == 1 && !last) {
-					// scatter_ray = Ray(at(t), dir, time); o += d * 0.001   Renderer.cu:168-175
-					v3 o2 = rt::madd(dir, 0.001f, s.p);
-					v3 t2 = rt::mulv(thr, att);
-					no = make_float4(o2.x, o2.y, o2.z, fo.w);
-					nd = make_float4(dir.x, dir.y, dir.z, fd.w);
-					nt = make_float4(t2.x, t2.y, t2.z, 0.0f);
-					alive = true;
-				}
-			}
+			alive = shade_segment(sv, bp, wv, batch, bounce, fo, fd, xyz(ft), __int_as_float(h.x), h.y, no, nd, nthr);
 		}
 		// live-path compaction: warp ballot/popc, one global atomic per block
 		const uint32_t mask = __ballot_sync(FULL_MASK, alive);
@@ -538,14 +609,56 @@ shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
 #pragma unroll
 			for (int w = 0; w < SHADE_THREADS / 32; ++w) { uint32_t c = s_warp[w]; s_warp[w] = tot; tot += c; }
 			s_base = tot ? atomicAdd(wv.n_live + bounce + 1, tot) : 0u;
+			s_chunk = (n > static_span) ? static_span + atomicAdd(counter, (uint32_t)SHADE_THREADS) : n;
 		}
 		__syncthreads();
 		if (alive) {
 			const uint32_t pos = s_base + s_warp[warp] + __popc(mask & ((1u << lane) - 1u));
-			wv.ray_o[out][pos] = no; wv.ray_d[out][pos] = nd; wv.thr[out][pos] = nt;
+			wo[pos] = no; wd[pos] = nd; wt[pos] = make_float4(nthr.x, nthr.y, nthr.z, 0.0f);
 		}
+		base = s_chunk;
 		__syncthreads();
 	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// tail: once the live queue is too short to fill the machine, per-bounce launches are pure latency.
+// One persistent launch then runs every remaining path to completion (traverse + shade fused, one
+// thread per path); later traverse/shade launches of the batch see tail_from and return at once.
+
+template <bool MEDIA>
+__global__ void __launch_bounds__(TRAVERSE_THREADS)
+tail_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce0, uint32_t threshold) {
+	__shared__ int s_stack[STACK_SIZE * TRAVERSE_THREADS];
+	if (*wv.tail_from < bounce0) return;                 // an earlier checkpoint already took the batch over
+	const uint32_t n = wv.n_live[bounce0];
+	if (n == 0 || n > threshold) return;
+	if (blockIdx.x == 0 && threadIdx.x == 0) *wv.tail_from = bounce0;
+	const uint32_t batch = *wv.batch_index;
+	const int in = bounce0 & 1;
+	const float4* __restrict__ ro = in ? wv.ray_o[1] : wv.ray_o[0];
+	const float4* __restrict__ rd = in ? wv.ray_d[1] : wv.ray_d[0];
+	const float4* __restrict__ rt_ = in ? wv.thr[1] : wv.thr[0];
+	unsigned long long extra = 0;
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		float4 fo = ro[i], fd = rd[i];
+		v3 thr = xyz(rt_[i]);
+		MediumRng mr{0, 0, 0, 0};
+		if (MEDIA) { mr.seed = bp.seed; path_pixel_sample(bp, batch, __float_as_uint(fd.w), mr.pixel, mr.sample); }
+		for (uint32_t b = bounce0; b < bp.max_depth; ++b) {
+			if (b > bounce0) ++extra;
+			mr.bounce = b;
+			float t; int code;
+			trace_ray<MEDIA>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code);
+			float4 no, nd; v3 nthr;
+			if (!shade_segment(sv, bp, wv, batch, b, fo, fd, thr, t, code, no, nd, nthr)) break;
+			fo = no; fd = nd; thr = nthr;
+		}
+	}
+	// ray segments traced beyond the first one of each path (that one is counted through n_live)
+	for (int off = 16; off > 0; off >>= 1) extra += __shfl_down_sync(FULL_MASK, extra, off);
+	if ((threadIdx.x & 31) == 0 && extra) atomicAdd(wv.totals + 1, extra);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -636,10 +749,10 @@ hit_record_kernel(SceneView sv, const float4* __restrict__ ro, const float4* __r
 			r.p[0] = r.p[1] = r.p[2] = 0.0f; r.n[0] = r.n[1] = r.n[2] = 0.0f;
 		} else {
 			const float4 fo = ro[i], fd = rd[i];
-			const int2 info = __ldg(sv.prim_info + (h.y >> 3));
+			const int2 info = __ldg(sv.prim_info + (h.y >> RTB_LEAF_TYPE_BITS));
 			Surface s;
 			reconstruct(sv, h.y, xyz(fo), xyz(fd), fo.w, r.t, true, s);
-			r.prim = h.y >> 3; r.object = info.y; r.material = info.x;
+			r.prim = h.y >> RTB_LEAF_TYPE_BITS; r.object = info.y; r.material = info.x;
 			r.p[0] = s.p.x; r.p[1] = s.p.y; r.p[2] = s.p.z;
 			r.n[0] = s.n_shade.x; r.n[1] = s.n_shade.y; r.n[2] = s.n_shade.z;
 			r.front_face = rt::dot(xyz(fd), s.n_geom) > 0.0f ? 0 : 1;
@@ -662,6 +775,12 @@ void query_occupancy(int device, LaunchCfg& lc) {
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, shade_kernel, SHADE_THREADS, 0);
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, generate_kernel, STREAM_THREADS, 0);
 	int occ_trav = occ_t < occ_tm ? occ_t : occ_tm;
+	int occ_l = 0, occ_lm = 0;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, tail_kernel<false>, TRAVERSE_THREADS, 0);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lm, tail_kernel<true>, TRAVERSE_THREADS, 0);
+	int occ_tail = occ_l < occ_lm ? occ_l : occ_lm;
+	lc.blocks_tail = sms * (occ_tail > 0 ? occ_tail : 1);
+	lc.sms = sms;
 	lc.blocks_traverse = sms * (occ_trav > 0 ? occ_trav : 1);
 	lc.blocks_shade = sms * (occ_s > 0 ? occ_s : 1);
 	lc.blocks_stream = sms * (occ_g > 0 ? occ_g : 1);
@@ -674,6 +793,10 @@ void launch_traverse(const SceneView& sv, const BatchParams& bp, const WaveView&
 	// media need the per-path RNG inside traversal; scenes without media skip that code entirely
 	if (sv.has_media) traverse_kernel<true><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce);
 	else traverse_kernel<false><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce);
+}
+void launch_tail(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, uint32_t threshold, const LaunchCfg& lc, cudaStream_t st) {
+	if (sv.has_media) tail_kernel<true><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, threshold);
+	else tail_kernel<false><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, threshold);
 }
 void launch_shade(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st) {
 	shade_kernel<<<lc.blocks_shade, SHADE_THREADS, 0, st>>>(sv, bp, wv, bounce);

@@ -17,6 +17,9 @@ struct SceneView {
 	const float4* materials;    // 2 x float4 per material
 	const float4* textures;     // 3 x float4 per texture
 	const uint8_t* blob;        // image texels / Perlin tables
+	const int32_t* pre_list;    // leaf codes of media tested before the BVH walk
+	int32_t n_pre;
+	int32_t bvh_empty;
 	int32_t root_ref;
 	int32_t n_prims;
 	int32_t has_media;          // selects the traverse variant that draws free-flight distances
@@ -46,13 +49,15 @@ struct WaveView {
 	uint32_t* n_live;           // [max_depth + 1] queue lengths per bounce
 	uint32_t* work;             // [2 * (max_depth + 1)] dynamic work counters (traverse, shade)
 	uint32_t* batch_index;      // device-side batch counter (graph replays need no new arguments)
+	uint32_t* tail_from;        // first bounce handled by the fused tail kernel (0xFFFFFFFF: none yet)
 	unsigned long long* totals; // [0] paths, [1] rays
 };
 
-struct LaunchCfg { int blocks_traverse, blocks_shade, blocks_stream; };
+struct LaunchCfg { int blocks_traverse, blocks_shade, blocks_stream, blocks_tail, sms; };
 
 void launch_generate(const BatchParams& bp, const rtb_camera& cam, const WaveView& wv, const LaunchCfg& lc, cudaStream_t st);
 void launch_traverse(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st);
+void launch_tail(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, uint32_t threshold, const LaunchCfg& lc, cudaStream_t st);
 void launch_shade(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st);
 void launch_accumulate(const BatchParams& bp, const WaveView& wv, float4* accum, float4* accum2, const LaunchCfg& lc, cudaStream_t st);
 void launch_resolve(const float4* accum, float4* out, uint32_t n, cudaStream_t st);

@@ -31,7 +31,7 @@ struct rtb_renderer {
 	bool timed = false;
 
 	// scene arena
-	void* d_scene = nullptr; size_t scene_bytes = 0;
+	void* d_scene = nullptr; size_t scene_bytes = 0, scene_upload_bytes = 0;
 	SceneView sv{};
 	bool has_scene = false;
 	uint64_t scene_version = 0;
@@ -53,6 +53,7 @@ struct rtb_renderer {
 	float4 *graph_accum = nullptr;
 
 	uint64_t launches = 0, batches = 0;
+	uint32_t tail_threshold = 0;   // live-queue length below which the fused tail kernel takes a batch over
 
 	// optional per-launch event timing (rtb_renderer_set_profiling)
 	bool profiling = false;
@@ -110,6 +111,8 @@ int rtb_renderer_create(rtb_renderer** out, int device) {
 	CUDA_TRY(cudaEventCreate(&r->ev_t0));
 	CUDA_TRY(cudaEventCreate(&r->ev_t1));
 	query_occupancy(device, r->lc);
+	r->tail_threshold = (uint32_t)r->lc.sms * 768u;   // ~6 warps of rays per SM sub-partition
+	if (const char* e = getenv("RTB_TAIL_THRESHOLD")) r->tail_threshold = (uint32_t)strtoul(e, nullptr, 10);
 	*out = r;
 	return RTB_OK;
 }
@@ -140,7 +143,8 @@ int rtb_renderer_set_scene(rtb_renderer* r, rtb_scene* s) {
 	size_t off_mats = align_up(off_info + fs.prim_info.size() * sizeof(DevPrimInfo), 256);
 	size_t off_texs = align_up(off_mats + fs.materials.size() * sizeof(DevMaterial), 256);
 	size_t off_blob = align_up(off_texs + fs.textures.size() * sizeof(DevTexture), 256);
-	size_t total = align_up(off_blob + fs.blob.size(), 256) + 256;
+	size_t off_pre = align_up(off_blob + fs.blob.size(), 256);
+	size_t total = align_up(off_pre + fs.pre_list.size() * 4, 256) + 256;
 	std::vector<uint8_t> staging(total, 0);
 	if (!fs.nodes.empty()) memcpy(staging.data() + off_nodes, fs.nodes.data(), fs.nodes.size() * sizeof(DevNode));
 	memcpy(staging.data() + off_prims, fs.prims.data(), fs.prims.size() * sizeof(DevPrim));
@@ -148,6 +152,7 @@ int rtb_renderer_set_scene(rtb_renderer* r, rtb_scene* s) {
 	if (!fs.materials.empty()) memcpy(staging.data() + off_mats, fs.materials.data(), fs.materials.size() * sizeof(DevMaterial));
 	if (!fs.textures.empty()) memcpy(staging.data() + off_texs, fs.textures.data(), fs.textures.size() * sizeof(DevTexture));
 	if (!fs.blob.empty()) memcpy(staging.data() + off_blob, fs.blob.data(), fs.blob.size());
+	if (!fs.pre_list.empty()) memcpy(staging.data() + off_pre, fs.pre_list.data(), fs.pre_list.size() * 4);
 	if (total > r->scene_bytes) {
 		cudaFree(r->d_scene); r->d_scene = nullptr; r->scene_bytes = 0;
 		CUDA_TRY(cudaMalloc(&r->d_scene, total));
@@ -161,15 +166,21 @@ int rtb_renderer_set_scene(rtb_renderer* r, rtb_scene* s) {
 	r->sv.materials = reinterpret_cast<const float4*>(base + off_mats);
 	r->sv.textures = reinterpret_cast<const float4*>(base + off_texs);
 	r->sv.blob = base + off_blob;
+	r->sv.pre_list = reinterpret_cast<const int32_t*>(base + off_pre);
+	r->sv.n_pre = (int32_t)fs.pre_list.size();
+	r->sv.bvh_empty = fs.bvh_empty;
 	r->sv.root_ref = fs.root_ref;
 	r->sv.n_prims = (int32_t)fs.prims.size();
 	r->sv.has_media = fs.n_media > 0;
 	r->sv.background_mode = fs.background_mode;
 	r->sv.bg_r = fs.background[0]; r->sv.bg_g = fs.background[1]; r->sv.bg_b = fs.background[2];
 	r->has_scene = true;
+	r->scene_upload_bytes = total;
 	r->scene_version++;
 	return RTB_OK;
 }
+
+size_t rtb_renderer_scene_bytes(const rtb_renderer* r) { return r ? r->scene_upload_bytes : 0; }
 
 int rtb_renderer_set_camera(rtb_renderer* r, const rtb_camera* cam) {
 	if (!r || !cam) return fail(RTB_ERR_INVALID, "rtb_renderer_set_camera: null argument");
@@ -214,14 +225,23 @@ static int ensure_wave(rtb_renderer* r, size_t paths, uint32_t depth) {
 	r->wv.thr[0] = (float4*)(b + o_t0); r->wv.thr[1] = (float4*)(b + o_t1);
 	r->wv.hit = (int2*)(b + o_hit); r->wv.contrib = (float4*)(b + o_con);
 	r->wv.n_live = (uint32_t*)(b + o_live); r->wv.work = (uint32_t*)(b + o_work);
-	r->wv.batch_index = (uint32_t*)(b + o_batch); r->wv.totals = (unsigned long long*)(b + o_tot);
+	r->wv.batch_index = (uint32_t*)(b + o_batch); r->wv.tail_from = r->wv.batch_index + 1; r->wv.totals = (unsigned long long*)(b + o_tot);
 	r->wave_paths = P; r->wave_depth = depth;
 	return RTB_OK;
 }
 
+// Bounces before which the fused tail kernel checks whether the live queue has become short.
+static bool tail_checkpoint(uint32_t b) {
+	static const uint32_t pts[] = {2, 3, 4, 5, 6, 8, 10, 12, 15, 18, 22, 27, 33, 40, 48, 58, 70, 85, 100};
+	for (uint32_t p : pts) if (p == b) return true;
+	return b > 100 && b % 25 == 0;
+}
+static uint32_t count_tail_checkpoints(uint32_t depth) { uint32_t c = 0; for (uint32_t b = 0; b < depth; ++b) c += tail_checkpoint(b) ? 1 : 0; return c; }
+
 static void enqueue_batch(rtb_renderer* r, const BatchParams& bp, cudaStream_t st) {
 	prof_begin(r, 0, st); launch_generate(bp, r->cam, r->wv, r->lc, st); prof_end(r, st);
 	for (uint32_t b = 0; b < bp.max_depth; ++b) {
+		if (r->tail_threshold && tail_checkpoint(b)) { prof_begin(r, 4, st); launch_tail(r->sv, bp, r->wv, b, r->tail_threshold, r->lc, st); prof_end(r, st); }
 		prof_begin(r, 1, st); launch_traverse(r->sv, bp, r->wv, b, r->lc, st); prof_end(r, st);
 		prof_begin(r, 2, st); launch_shade(r->sv, bp, r->wv, b, r->lc, st); prof_end(r, st);
 	}
@@ -244,11 +264,12 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 
 	const uint32_t spp = p->sample_end - p->sample_begin;
 	const uint64_t npix = (uint64_t)p->width * (row_end - row_begin);
-	uint64_t target_paths = 8ull << 20;
+	uint64_t target_paths = 16ull << 20;
 	if (const char* e = getenv("RTB_BATCH_PATHS")) { uint64_t v = strtoull(e, nullptr, 10); if (v > 0) target_paths = v; }
 	uint64_t S = p->samples_per_batch ? p->samples_per_batch : target_paths / npix;
 	if (S < 1) S = 1;
 	if (S > spp) S = spp ? spp : 1;
+	if (!p->samples_per_batch && spp) { uint64_t nb = (spp + S - 1) / S; S = (spp + nb - 1) / nb; }   // equal-sized batches
 	if (npix * S >= (1ull << 31)) return fail(RTB_ERR_INVALID, "rtb_render: batch too large (lower samples_per_batch)");
 	rc = ensure_wave(r, (size_t)(npix * S), p->max_depth);
 	if (rc) return rc;
@@ -273,7 +294,7 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 	CUDA_TRY(cudaEventRecord(r->ev_t0, st));
 
 	const uint32_t n_batches = spp ? (uint32_t)((spp + S - 1) / S) : 0;
-	const uint64_t launches_per_batch = 3 + 2ull * bp.max_depth;
+	const uint64_t launches_per_batch = 3 + 2ull * bp.max_depth + (r->tail_threshold ? count_tail_checkpoints(bp.max_depth) : 0);
 	const bool use_graph = getenv("RTB_NO_GRAPH") == nullptr && n_batches > 0 && !r->profiling;
 	if (use_graph) {
 		bool reuse = r->graph_valid && memcmp(&r->graph_bp, &bp, sizeof bp) == 0 && memcmp(&r->graph_cam, &r->cam, sizeof r->cam) == 0 &&
@@ -378,13 +399,14 @@ int rtb_get_profile(rtb_renderer* r, rtb_profile* out) {
 	memset(out, 0, sizeof *out);
 	CUDA_TRY(cudaSetDevice(r->device));
 	CUDA_TRY(cudaStreamSynchronize(r->stream));
-	double ms[4] = {0, 0, 0, 0}; uint64_t cnt[4] = {0, 0, 0, 0};
+	double ms[5] = {0, 0, 0, 0, 0}; uint64_t cnt[5] = {0, 0, 0, 0, 0};
 	for (size_t i = 0; i < r->prof_used; ++i) {
 		float t = 0.0f;
 		CUDA_TRY(cudaEventElapsedTime(&t, r->prof_events[2 * i], r->prof_events[2 * i + 1]));
 		ms[r->prof_class[i]] += t; cnt[r->prof_class[i]]++;
 	}
 	out->generate_ms = ms[0]; out->traverse_ms = ms[1]; out->shade_ms = ms[2]; out->accumulate_ms = ms[3];
+	out->tail_ms = ms[4]; out->tail_launches = cnt[4];
 	out->generate_launches = cnt[0]; out->traverse_launches = cnt[1]; out->shade_launches = cnt[2]; out->accumulate_launches = 2 * cnt[3];
 	r->prof_used = 0;
 	return RTB_OK;

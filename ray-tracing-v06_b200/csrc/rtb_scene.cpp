@@ -604,35 +604,62 @@ namespace {
 struct Flattener {
 	rtb_scene& s;
 	FlatScene& out;
+	// One item per logical primitive (= one BVH leaf); an item owns one or two 64-byte record slots.
+	struct Item { DevPrim rec[2]; int nrec; int type; DevPrimInfo info; };
+	std::vector<Item> items;
 	std::vector<Box3> prim_boxes;
-	std::string err;
 
-	void emit(int type, const DevPrim& p, const Box3& b, int mat, int obj) {
-		out.prims.push_back(p); out.prim_type.push_back(type);
-		DevPrimInfo pi; pi.material = mat; pi.object = obj; out.prim_info.push_back(pi);
+	void emit(int type, const DevPrim& p, const Box3& b, int mat, int obj, const DevPrim* second = nullptr) {
+		Item it{}; it.rec[0] = p; it.nrec = 1; it.type = type; it.info.material = mat; it.info.object = obj;
+		if (second) { it.rec[1] = *second; it.nrec = 2; }
+		items.push_back(it);
 		prim_boxes.push_back(b);
+	}
+	static bool is_identity(const Xf& x) { return !x.rot && !x.tr; }
+	static void put_xf(float* q, const Xf& x) {   // (cos, sin, off.x, off.y), (off.z, 0, 0, 0)
+		q[0] = x.rot ? x.c : 1.0f; q[1] = x.rot ? x.s : 0.0f; q[2] = x.off[0]; q[3] = x.off[1]; q[4] = x.off[2];
+	}
+	// World bounds of an instanced primitive are computed with host rounding, the hit with the
+	// kernel's ray transform: pad so the box always contains what the kernel can hit.
+	static void pad_instance_box(Box3& b) {
+		for (int i = 0; i < 3; ++i) {
+			float m = std::fmax(std::fabs(b.mn[i]), std::fabs(b.mx[i]));
+			float e = std::fmax(1e-4f, 4e-6f * m);
+			b.mn[i] -= e; b.mx[i] += e;
+		}
 	}
 	void emit_sphere(const rtbs_object& o, int id, const Xf& x) {
 		float c[3]; x.point(o.f, c);
-		DevPrim p{}; p.q[0] = c[0]; p.q[1] = c[1]; p.q[2] = c[2]; p.q[3] = o.f[3];
-		p.q[4] = x.rot ? x.c : 1.0f; p.q[5] = x.rot ? x.s : 0.0f;   // instance rotation, for get_sphere_uv in the object frame
+		DevPrim p{};
 		Box3 b; for (int i = 0; i < 3; ++i) { b.mn[i] = c[i] - o.f[3]; b.mx[i] = c[i] + o.f[3]; }
-		emit(PRIM_SPHERE, p, b, o.mat, id);
+		if (is_identity(x)) {
+			p.q[0] = c[0]; p.q[1] = c[1]; p.q[2] = c[2]; p.q[3] = o.f[3];
+			emit(PRIM_SPHERE, p, b, o.mat, id);
+		} else {
+			p.q[0] = o.f[0]; p.q[1] = o.f[1]; p.q[2] = o.f[2]; p.q[3] = o.f[3];
+			put_xf(p.q + 4, x); pad_instance_box(b);
+			emit(PRIM_SPHERE | PRIM_XF, p, b, o.mat, id);
+		}
 	}
 	void emit_moving_sphere(const rtbs_object& o, int id, const Xf& x) {
 		float c0[3], c1[3]; x.point(o.f, c0); x.point(o.f + 4, c1);
-		DevPrim p{}; p.q[0] = c0[0]; p.q[1] = c0[1]; p.q[2] = c0[2]; p.q[3] = o.f[3]; p.q[4] = c1[0]; p.q[5] = c1[1]; p.q[6] = c1[2];
-		p.q[8] = x.rot ? x.c : 1.0f; p.q[9] = x.rot ? x.s : 0.0f;
+		DevPrim p{};
 		Box3 b;
 		for (int i = 0; i < 3; ++i) {
 			float a0 = c0[i] - o.f[3], a1 = c1[i] - o.f[3], b0 = c0[i] + o.f[3], b1 = c1[i] + o.f[3];
 			b.mn[i] = (a1 < a0) ? a1 : a0; b.mx[i] = (b0 < b1) ? b1 : b0;
 		}
-		emit(PRIM_MOVING_SPHERE, p, b, o.mat, id);
+		if (is_identity(x)) {
+			p.q[0] = c0[0]; p.q[1] = c0[1]; p.q[2] = c0[2]; p.q[3] = o.f[3]; p.q[4] = c1[0]; p.q[5] = c1[1]; p.q[6] = c1[2];
+			emit(PRIM_MOVING_SPHERE, p, b, o.mat, id);
+		} else {
+			p.q[0] = o.f[0]; p.q[1] = o.f[1]; p.q[2] = o.f[2]; p.q[3] = o.f[3]; p.q[4] = o.f[4]; p.q[5] = o.f[5]; p.q[6] = o.f[6];
+			put_xf(p.q + 8, x); pad_instance_box(b);
+			emit(PRIM_MOVING_SPHERE | PRIM_XF, p, b, o.mat, id);
+		}
 	}
-	void emit_planar(int type, const float Q0[3], const float u0[3], const float v0[3], int mat, int id, const Xf& x) {
-		float Q[3], u[3], v[3]; x.point(Q0, Q); x.vec(u0, u); x.vec(v0, v);
-		// book quad ctor: n = cross(u,v); normal = unit(n); D = dot(normal,Q); w = n / dot(n,n)
+	void emit_planar(int type, const float Q[3], const float u[3], const float v[3], int mat, int id, const Xf& x) {
+		// book quad ctor, in the primitive's own frame: n = cross(u,v); normal = unit(n); D = dot(normal,Q); w = n / dot(n,n)
 		rt::v3 U = rt::mk(u[0], u[1], u[2]), V = rt::mk(v[0], v[1], v[2]), QQ = rt::mk(Q[0], Q[1], Q[2]);
 		rt::v3 n = rt::cross(U, V);
 		rt::v3 N = rt::normalize(n);
@@ -645,14 +672,23 @@ struct Flattener {
 		p.q[12] = w.x; p.q[13] = w.y; p.q[14] = w.z; p.q[15] = N.z;
 		float f[9]; memcpy(f, Q, 12); memcpy(f + 3, u, 12); memcpy(f + 6, v, 12);
 		float pts[4][3]; quad_corners(f, pts);
-		Box3 b = box_of_points(pts, type == PRIM_QUAD ? 4 : 3); pad_to_minimum(b);
-		emit(type, p, b, mat, id);
+		const int cnt = type == PRIM_QUAD ? 4 : 3;
+		if (is_identity(x)) {
+			Box3 b = box_of_points(pts, cnt); pad_to_minimum(b);
+			emit(type, p, b, mat, id);
+		} else {
+			float wp[4][3];
+			for (int i = 0; i < cnt; ++i) x.point(pts[i], wp[i]);
+			Box3 b = box_of_points(wp, cnt); pad_to_minimum(b); pad_instance_box(b);
+			DevPrim t{}; put_xf(t.q, x);          // second slot: the transform
+			emit(type | PRIM_XF, p, b, mat, id, &t);
+		}
 	}
 	void emit_box(const rtbs_object& o, int id, const Xf& x) {
 		// book box(a,b): six quads with outward normals (front, right, back, left, top, bottom)
 		const float* mn = o.f; const float* mx = o.f + 3;
 		float dx[3] = {mx[0] - mn[0], 0, 0}, dy[3] = {0, mx[1] - mn[1], 0}, dz[3] = {0, 0, mx[2] - mn[2]};
-		float ndx[3] = {-dx[0], 0, 0}, ndz[3] = {0, 0, -dz[2]};
+		float ndx[3] = {-dx[0], -dx[1], -dx[2]}, ndz[3] = {-dz[0], -dz[1], -dz[2]};   // full negation (signed zeros as in -dx)
 		float q0[3] = {mn[0], mn[1], mx[2]}; emit_planar(PRIM_QUAD, q0, dx, dy, o.mat, id, x);
 		float q1[3] = {mx[0], mn[1], mx[2]}; emit_planar(PRIM_QUAD, q1, ndz, dy, o.mat, id, x);
 		float q2[3] = {mx[0], mn[1], mn[2]}; emit_planar(PRIM_QUAD, q2, ndx, dy, o.mat, id, x);
@@ -733,12 +769,37 @@ int flatten(rtb_scene& s, FlatScene& out) {
 	Xf ident;
 	int rc = fl.walk(s.root, ident, 0);
 	if (rc) return rc;
-	if (out.prims.empty()) return fail(RTB_ERR_INVALID, "scene has no primitives");
-	if (out.prims.size() >= (1u << 28)) return fail(RTB_ERR_UNSUPPORTED, "too many primitives");
+	if (fl.items.empty()) return fail(RTB_ERR_INVALID, "scene has no primitives");
+	if (fl.items.size() >= (1u << 26)) return fail(RTB_ERR_UNSUPPORTED, "too many primitives");
+
+	// Participating media are tested BEFORE the BVH walk (at most 8, the largest first): a ray inside a
+	// medium then starts traversal with a tight t bound instead of wading through every box that
+	// happens to contain its origin.  Closest-hit results do not depend on the test order.
+	{
+		std::vector<int> media;
+		for (size_t i = 0; i < fl.items.size(); ++i) if (fl.items[i].type == PRIM_MEDIUM_SPHERE || fl.items[i].type == PRIM_MEDIUM_BOX) media.push_back((int)i);
+		std::stable_sort(media.begin(), media.end(), [&](int a, int b) { return surface_area(fl.prim_boxes[a]) > surface_area(fl.prim_boxes[b]); });
+		if (media.size() > 8) media.resize(8);
+		std::vector<char> is_pre(fl.items.size(), 0);
+		for (int m : media) is_pre[m] = 1;
+		std::vector<Flattener::Item> rest; std::vector<Box3> rest_boxes;
+		for (int m : media) {
+			const Flattener::Item& it = fl.items[m];
+			out.pre_list.push_back((int32_t)(((int)out.prims.size() << RTB_LEAF_TYPE_BITS) | it.type));
+			for (int k = 0; k < it.nrec; ++k) { out.prims.push_back(it.rec[k]); out.prim_info.push_back(it.info); out.prim_type.push_back(k == 0 ? it.type : -1); }
+		}
+		for (size_t i = 0; i < fl.items.size(); ++i) if (!is_pre[i]) { rest.push_back(fl.items[i]); rest_boxes.push_back(fl.prim_boxes[i]); }
+		fl.items.swap(rest); fl.prim_boxes.swap(rest_boxes);
+	}
+	if (fl.items.empty()) {   // nothing but pre-tested media: no BVH at all
+		out.bvh_empty = 1; out.root_ref = 0; out.max_depth_nodes = 0;
+		s.world_nodes.clear(); s.world_root = -1;
+	}
 
 	// World BVH.  A root that is a reference BVH keeps the reference's builder (and therefore its
 	// exact node / primitive order); anything else gets the quality SAH builder.
 	const rtbs_object& root = s.objects[s.root];
+	if (!out.bvh_empty) {
 	std::vector<rtb_bvh_node> nodes; std::vector<int> order; int root_idx = -1;
 	const int STACK_LIMIT = 30;
 	bool built = false;
@@ -757,19 +818,21 @@ int flatten(rtb_scene& s, FlatScene& out) {
 	}
 	out.max_depth_nodes = bvh_depth(nodes, root_idx);
 
-	// Reorder primitives into BVH leaf order (Factory::hittables, BVH.cu:174-177).
-	{
-		std::vector<DevPrim> prims(out.prims.size()); std::vector<DevPrimInfo> info(out.prims.size()); std::vector<int32_t> type(out.prims.size());
-		for (size_t i = 0; i < order.size(); ++i) { prims[i] = out.prims[order[i]]; info[i] = out.prim_info[order[i]]; type[i] = out.prim_type[order[i]]; }
-		out.prims.swap(prims); out.prim_info.swap(info); out.prim_type.swap(type);
+	// Lay the records out in BVH leaf order (Factory::hittables, BVH.cu:174-177); a leaf refers to
+	// the first record slot of its item.
+	std::vector<int> slot_of(order.size()), type_of(order.size());
+	for (size_t i = 0; i < order.size(); ++i) {
+		const Flattener::Item& it = fl.items[order[i]];
+		slot_of[i] = (int)out.prims.size(); type_of[i] = it.type;
+		for (int k = 0; k < it.nrec; ++k) { out.prims.push_back(it.rec[k]); out.prim_info.push_back(it.info); out.prim_type.push_back(k == 0 ? it.type : -1); }
 	}
 	s.world_nodes = nodes; s.world_root = root_idx;
 
 	// Wide layout: one 64-byte record per inner node carrying both children's boxes, numbered in
 	// depth-first pre-order (root = 0) so the near part of a subtree is contiguous.
+	auto leaf_ref = [&](int node) { int item = nodes[node].right_child_hittable_idx; return make_leaf_ref(slot_of[item], type_of[item]); };
 	if (nodes[root_idx].left_child_idx == -1) {
-		int prim = nodes[root_idx].right_child_hittable_idx;
-		out.root_ref = make_leaf_ref(prim, out.prim_type[prim]);
+		out.root_ref = leaf_ref(root_idx);
 	} else {
 		std::vector<int> dev_index(nodes.size(), -1);
 		std::vector<int> stack; stack.push_back(root_idx); int next = 0;
@@ -782,10 +845,7 @@ int flatten(rtb_scene& s, FlatScene& out) {
 			stack.push_back(nodes[i].left_child_idx);
 		}
 		out.nodes.resize(inner_order.size());
-		auto ref_of = [&](int i) {
-			if (nodes[i].left_child_idx == -1) { int prim = nodes[i].right_child_hittable_idx; return make_leaf_ref(prim, out.prim_type[prim]); }
-			return dev_index[i];
-		};
+		auto ref_of = [&](int i) { return nodes[i].left_child_idx == -1 ? leaf_ref(i) : dev_index[i]; };
 		for (int i : inner_order) {
 			const rtb_bvh_node& l = nodes[nodes[i].left_child_idx];
 			const rtb_bvh_node& r = nodes[nodes[i].right_child_hittable_idx];
@@ -795,6 +855,8 @@ int flatten(rtb_scene& s, FlatScene& out) {
 			d.left = ref_of(nodes[i].left_child_idx); d.right = ref_of(nodes[i].right_child_hittable_idx); d.pad0 = d.pad1 = 0;
 		}
 		out.root_ref = 0;
+	}
+
 	}
 
 	// Materials / textures.
@@ -819,6 +881,16 @@ int flatten(rtb_scene& s, FlatScene& out) {
 }
 
 }  // namespace rtb
+
+extern "C" int rtb_scene_flatten_stats(rtb_scene* s, int32_t out4[4]) {
+	if (!s || !out4) return rtb::fail(RTB_ERR_INVALID, "rtb_scene_flatten_stats: null argument");
+	rtb::FlatScene fs;
+	int rc = rtb::flatten(*s, fs);
+	if (rc) return rc;
+	out4[0] = (int32_t)((s->world_nodes.size() + 1) / 2); out4[1] = (int32_t)fs.prims.size();
+	out4[2] = (int32_t)fs.nodes.size(); out4[3] = fs.max_depth_nodes;
+	return RTB_OK;
+}
 
 // ============================================================== cameras (cu_Cameras.cuh ctors restated, host arithmetic)
 

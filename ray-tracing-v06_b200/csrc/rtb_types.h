@@ -8,15 +8,20 @@
 
 namespace rtb {
 
-// Primitive types (3 bits of a leaf reference).
+// Primitive types (4 bits of a leaf reference): a base type, plus PRIM_XF when the primitive is an
+// instance (translate / rotate_y chain): its record then holds OBJECT-space geometry followed by
+// the world-from-object transform, and the kernels transform the ray exactly like the book's
+// translate::hit / rotate_y::hit do (so instanced hits are bit-exact against the oracle too).
 enum PrimType : int {
 	PRIM_SPHERE = 0, PRIM_MOVING_SPHERE = 1, PRIM_QUAD = 2, PRIM_TRIANGLE = 3,
-	PRIM_MEDIUM_SPHERE = 4, PRIM_MEDIUM_BOX = 5
+	PRIM_MEDIUM_SPHERE = 4, PRIM_MEDIUM_BOX = 5,
+	PRIM_XF = 8
 };
+#define RTB_LEAF_TYPE_BITS 4
 
 // Child reference of a wide-layout BVH node: >= 0 inner node index; < 0 leaf,
-// ~ref = (prim_index << 3) | PrimType.
-inline int make_leaf_ref(int prim, int type) { return ~((prim << 3) | type); }
+// ~ref = (prim_index << 4) | PrimType.
+inline int make_leaf_ref(int prim, int type) { return ~((prim << RTB_LEAF_TYPE_BITS) | type); }
 
 // 64-byte inner node holding BOTH children's boxes, fetched as 4 x LDG.128:
 //   a = (l.min.x, l.min.y, l.min.z, l.max.x)   b = (l.max.y, l.max.z, r.min.x, r.min.y)
@@ -24,12 +29,14 @@ inline int make_leaf_ref(int prim, int type) { return ~((prim << 3) | type); }
 struct alignas(64) DevNode { float f[12]; int32_t left, right, pad0, pad1; };
 
 // 64-byte primitive record (4 x float4):
-//   SPHERE         q0 = (c.xyz, r)        q1 = (cos, sin, 0, 0) of the baked rotate_y (uv frame)
-//   MOVING_SPHERE  q0 = (c0.xyz, r)       q1 = (c1.xyz, 0)   q2 = (cos, sin, 0, 0)
+//   SPHERE         q0 = (c.xyz, r)
+//   MOVING_SPHERE  q0 = (c0.xyz, r)       q1 = (c1.xyz, 0)
 //   QUAD/TRIANGLE  q0 = (Q.xyz, D)        q1 = (u.xyz, N.x)  q2 = (v.xyz, N.y)  q3 = (w.xyz, N.z)
 //   MEDIUM_SPHERE  q0 = (c.xyz, r)        q1 = (-1/density, medium index bits, 0, 0)
 //   MEDIUM_BOX     q0 = (bmin.xyz, cos)   q1 = (bmax.xyz, sin)  q2 = (offset.xyz, -1/density)
 //                  q3 = (medium index bits, 0, 0, 0)       world = R_y * object + offset
+// PRIM_XF variants append the transform T = (cos, sin, off.x, off.y), (off.z, 0, 0, 0):
+//   XF SPHERE at q1,q2; XF MOVING_SPHERE at q2,q3; XF QUAD/TRIANGLE in a second record slot (q4,q5).
 struct alignas(64) DevPrim { float q[16]; };
 
 struct alignas(8) DevPrimInfo { int32_t material; int32_t object; };
@@ -46,6 +53,8 @@ struct alignas(16) DevTexture {                                                 
 struct FlatScene {
 	std::vector<DevNode> nodes;          // wide layout actually traversed
 	int32_t root_ref = 0;                // inner index or leaf ref
+	int32_t bvh_empty = 0;               // every primitive is in pre_list
+	std::vector<int32_t> pre_list;       // leaf codes of the media tested before the BVH walk
 	std::vector<DevPrim> prims;
 	std::vector<DevPrimInfo> prim_info;
 	std::vector<int32_t> prim_type;

@@ -22,17 +22,23 @@ def _compare_hits(rtb, g, o, exact=True, rtol=1e-5):
     miss_g = g["object"] < 0; miss_o = o["object"] < 0
     assert np.array_equal(miss_g, miss_o), f"hit/miss differs on {(miss_g != miss_o).sum()} rays"
     hit = ~miss_g
-    assert np.array_equal(g["object"][hit], o["object"][hit])
-    assert np.array_equal(g["material"][hit], o["material"][hit])
-    assert np.array_equal(g["front_face"][hit], o["front_face"][hit])
+    # Two primitives hit at exactly the same t (coplanar faces of adjacent boxes, a box standing on the
+    # floor) are a tie: which one "t < rec.distance" keeps depends on traversal order.  Everything else
+    # must name the same object.
+    diff_obj = hit & (g["object"] != o["object"])
+    assert np.array_equal(g["t"][diff_obj].view(np.uint32), o["t"][diff_obj].view(np.uint32)), "different object at a different t"
+    assert diff_obj.sum() <= 0.01 * hit.sum(), f"{diff_obj.sum()} ties out of {hit.sum()} hits"
+    same = hit & ~diff_obj
+    assert np.array_equal(g["material"][same], o["material"][same])
+    assert np.array_equal(g["front_face"][same], o["front_face"][same])
     if exact:
         assert np.array_equal(g["t"][hit].view(np.uint32), o["t"][hit].view(np.uint32)), "t not bit-exact"
         assert np.array_equal(g["p"][hit].view(np.uint32), o["p"][hit].view(np.uint32)), "p not bit-exact"
-        assert np.array_equal(g["n"][hit].view(np.uint32), o["n"][hit].view(np.uint32)), "n not bit-exact"
+        assert np.array_equal(g["n"][same].view(np.uint32), o["n"][same].view(np.uint32)), "n not bit-exact"
     else:
         np.testing.assert_allclose(g["t"][hit], o["t"][hit], rtol=rtol)
         np.testing.assert_allclose(g["p"][hit], o["p"][hit], rtol=rtol, atol=rtol * 10)
-        np.testing.assert_allclose(g["n"][hit], o["n"][hit], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(g["n"][same], o["n"][same], rtol=0, atol=2e-5)
     return int(hit.sum())
 
 
@@ -71,20 +77,42 @@ def test_hit_records_bit_exact(rtb, orc, renderer, name, lo, hi):
 
 
 @pytest.mark.parametrize("name,lo,hi", [("book2_cornell", 0, 555), ("book2_final", -200, 600)])
-def test_hit_records_instanced(rtb, orc, renderer, name, lo, hi):
-    """Instances are baked into world space by the flattener while the oracle transforms the ray
-    (book translate / rotate_y): identical geometry, different rounding -> 1e-5 relative."""
+def test_hit_records_instanced_bit_exact(rtb, orc, renderer, name, lo, hi):
+    """translate(rotate_y(x)) instances: the kernels take the ray into the primitive's frame with the
+    same operations as the book's translate::hit / rotate_y::hit, so hits stay bit-exact."""
     scene = rtb.Scene.named(name)
     renderer.set_scene(scene)
     rays = np.concatenate([camera_rays(rtb, scene.info.camera, 200, 200, "renderer"), random_rays(rtb, 100_000, lo, hi, seed=11)])
     g = renderer.trace_rays(rays)
     o = _oracle_scene(orc, scene).trace_rays(rays, rtb.HIT_DTYPE)
-    same = (g["object"] == o["object"])
+    assert _compare_hits(rtb, g, o, exact=True) > 10_000
+
+
+def test_hit_records_nested_instances(rtb, orc, renderer):
+    """Deeper chains (rotate(translate(rotate(...)))) are composed into one transform by the flattener
+    while the oracle applies them one by one: same geometry, different rounding."""
+    s = rtb.Scene()
+    m = s.lambertian(albedo=(0.5, 0.5, 0.5))
+    box = s.box((0, 0, 0), (30, 60, 30), m)
+    sph = s.sphere((10, 70, 10), 12.0, m)
+    tri = s.triangle((0, 0, 40), (30, 0, 0), (0, 30, 0), m)
+    grp = s.list([box, sph, tri])
+    inst = s.rotate_y(s.translate(s.rotate_y(grp, 25.0), (40, 5, -20)), -40.0)
+    inst2 = s.translate(s.rotate_y(grp, 200.0), (-60, 0, 30))
+    s.set_root(s.list([inst, inst2, s.quad((-200, -1, -200), (400, 0, 0), (0, 0, 400), m)]))
+    renderer.set_scene(s)
+    rays = random_rays(rtb, 200_000, -120, 120, seed=3)
+    g = renderer.trace_rays(rays)
+    o = _oracle_scene(orc, s).trace_rays(rays, rtb.HIT_DTYPE)
+    same = g["object"] == o["object"]
     assert same.mean() > 0.9995, f"closest object agrees on {same.mean():.6f}"
     hit = same & (g["object"] >= 0)
+    assert hit.sum() > 20_000
     rel = np.abs(g["t"][hit] - o["t"][hit]) / np.abs(o["t"][hit])
-    assert np.quantile(rel, 0.999) < 1e-5, f"t relative error q99.9 {np.quantile(rel, 0.999):.2e}"
+    print(f"nested instances: t rel err median {np.median(rel):.2e} q99 {np.quantile(rel, 0.99):.2e} q99.9 {np.quantile(rel, 0.999):.2e} max {rel.max():.2e}")
+    assert np.quantile(rel, 0.99) < 1e-5
     assert np.abs(g["n"][hit] - o["n"][hit]).max() < 1e-3
+    assert np.array_equal(g["front_face"][hit], o["front_face"][hit]) or (g["front_face"][hit] != o["front_face"][hit]).mean() < 1e-4
 
 
 IMAGE_CASES = [
@@ -96,9 +124,9 @@ IMAGE_CASES = [
     ("book2_perlin", 160, 90, 4, 50, 0.01),
     ("book2_quads", 120, 120, 4, 50, 0.01),
     ("book2_simple_light", 160, 90, 8, 50, 0.01),
-    ("book2_cornell", 100, 100, 8, 50, 0.05),
-    ("book2_cornell_smoke", 100, 100, 8, 50, 0.05),
-    ("book2_final", 100, 100, 8, 40, 0.05),
+    ("book2_cornell", 100, 100, 8, 50, 0.01),
+    ("book2_cornell_smoke", 100, 100, 8, 50, 0.02),
+    ("book2_final", 100, 100, 8, 40, 0.02),
 ]
 
 
