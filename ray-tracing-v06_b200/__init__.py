@@ -204,6 +204,17 @@ def make_camera(kind: str, lookfrom, lookat, up=(0, 1, 0), vfov=40.0, aspect=1.0
     return cam
 
 
+def sample_range(spp_total: int, rank: int, world: int) -> tuple[int, int]:
+    """Sample-range partition of a render job: rank r of `world` renders samples [begin, end) of every pixel.
+    Contiguous, covers [0, spp_total) exactly, sizes differ by at most one."""
+    return (spp_total * rank) // world, (spp_total * (rank + 1)) // world
+
+
+def row_range(height: int, rank: int, world: int) -> tuple[int, int]:
+    """Image-tile (row band) partition, for renders that are split by tile instead of by sample range."""
+    return (height * rank) // world, (height * (rank + 1)) // world
+
+
 def bvh_build(aabbs: np.ndarray, builder: int = BVH_TOPDOWN_MEDIAN):
     """rtb_bvh_build: (nodes, order, root) exactly as BVH_Handle::Factory produces them."""
     a = np.ascontiguousarray(aabbs, dtype=np.float32).reshape(-1, 6)

@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Regenerates the golden fixtures in this directory from the REFERENCE itself.
+
+Needs /root/reference (build container) for `make -C oracle ref`, and a GPU for the megakernel part:
+
+  # CPU part (here): the reference's own BVH_Handle::Factory on the bouncing-spheres boxes
+  python tests/golden/make_golden.py bvh
+
+  # GPU part (on a B200 box; oracle/_ref/ref_render is the reference's Renderer.cu/BVH.cu/
+  # SphereHittable.cu/Scenes.cu/cuHostRND.cpp compiled unmodified for sm_100a):
+  gpurun -- 'oracle/_ref/ref_render rng gpurun_out/ref_rng.bin;
+             oracle/_ref/ref_render scene gpurun_out/ref_scene.bin;
+             oracle/_ref/ref_render render 200 112 4 50 gpurun_out/ref_img_200x112_4spp_d50.bin;
+             oracle/_ref/ref_render render 400 225 100 50 gpurun_out/ref_img_400x225_100spp_d50.bin'
+  python tests/golden/make_golden.py collect      # copies / converts gpurun_out/* into tests/golden/
+
+Fixtures:
+  ref_rng.bin                              4608 uniforms of the reference's cuHostRND(512,1984) + 4 x 64 device XORWOW uniforms
+  ref_scene_book2_bouncing.bin             the 488 spheres + material bytes the reference's Scenes.cu built on the GPU box
+  ref_megakernel_200x112_4spp_d50.bin      raw float4 framebuffer of the reference's render_kernel (first Render call)
+  ref_megakernel_400x225_100spp_d50_f16.npy  same at config 2's size, stored as float16 RGB
+  ref_bvh_book2_bouncing.bin               node array + primitive order of the reference's BuildBVH_TopDown
+"""
+import importlib
+import shutil
+import struct
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+GOLD = ROOT / "tests" / "golden"
+sys.path.insert(0, str(ROOT))
+
+
+def bvh():
+    rtb = importlib.import_module("ray-tracing-v06_b200")
+    s = rtb.Scene.named("book2_bouncing")
+    boxes = np.array([s.bounds(i) for i in range(488)], dtype=np.float32)
+    tmp_in, tmp_out = "/tmp/ref_bvh_in.bin", "/tmp/ref_bvh_out.bin"
+    open(tmp_in, "wb").write(struct.pack("i", len(boxes)) + boxes.tobytes())
+    subprocess.run([str(ROOT / "oracle" / "_ref" / "ref_bvh"), tmp_in, tmp_out, "0"], check=True)
+    shutil.copy(tmp_out, GOLD / "ref_bvh_book2_bouncing.bin")
+    print("wrote", GOLD / "ref_bvh_book2_bouncing.bin")
+
+
+def collect():
+    out = ROOT / "gpurun_out"
+    shutil.copy(out / "ref_rng.bin", GOLD / "ref_rng.bin")
+    shutil.copy(out / "ref_scene.bin", GOLD / "ref_scene_book2_bouncing.bin")
+    shutil.copy(out / "ref_img_200x112_4spp_d50.bin", GOLD / "ref_megakernel_200x112_4spp_d50.bin")
+    a = np.fromfile(out / "ref_img_400x225_100spp_d50.bin", dtype=np.float32).reshape(225, 400, 4)[..., :3]
+    np.save(GOLD / "ref_megakernel_400x225_100spp_d50_f16.npy", a.astype(np.float16))
+
+
+if __name__ == "__main__":
+    {"bvh": bvh, "collect": collect}[sys.argv[1]]()

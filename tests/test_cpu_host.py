@@ -1,0 +1,123 @@
+"""CPU tests of the host side: the C ABI surface, the scene graph, the flattener and the host mirror."""
+import ctypes as C
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from helpers import parse_blob
+
+
+def _header_functions():
+    text = (ROOT / "include" / "rtb.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rtb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(rtb):
+    names = _header_functions()
+    assert len(names) >= 50
+    lib = C.CDLL(str(rtb.LIB_PATH))
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in include/rtb.h but not exported: {missing}"
+    assert set(names) == set(rtb.ABI.keys()), set(names) ^ set(rtb.ABI.keys())
+    assert lib.rtb_abi_version() == 1
+
+
+def test_no_cpu_fallback(rtb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert rtb.lib().rtb_device_count() == 0
+    with pytest.raises(rtb.RtbError, match="no usable CUDA device"):
+        rtb.Renderer(0)
+
+
+def test_product_never_touches_the_oracle():
+    for path in (ROOT / "ray-tracing-v06_b200").rglob("*"):
+        if path.suffix in (".py", ".cpp", ".cu", ".h", ".cuh", ".hpp") or path.name == "Makefile":
+            text = path.read_text(errors="ignore")
+            assert "pyoracle" not in text and "liboracle" not in text and "oracle/" not in text.replace("(oracle/,", ""), path
+
+
+def test_scene_validation(rtb):
+    s = rtb.Scene()
+    with pytest.raises(rtb.RtbError):
+        s.sphere((0, 0, 0), 1.0, 0)                 # no such material
+    m = s.lambertian(albedo=(1, 0, 0))
+    with pytest.raises(rtb.RtbError):
+        s.lambertian(tex=3)
+    with pytest.raises(rtb.RtbError):
+        s.checker(0.0, 0, 0)
+    with pytest.raises(rtb.RtbError):
+        s.bvh([])
+    with pytest.raises(rtb.RtbError):
+        s.list([42])
+    with pytest.raises(rtb.RtbError):
+        s.set_root(7)
+    a = s.sphere((0, 0, 0), 1.0, m)
+    with pytest.raises(rtb.RtbError):
+        s.constant_medium(a, -1.0, m)
+    with pytest.raises(rtb.RtbError):
+        s.flatten_stats()                           # no root yet
+    q = s.quad((0, 0, 0), (1, 0, 0), (0, 1, 0), m)
+    med = s.constant_medium(q, 1.0, s.isotropic(s.solid((1, 1, 1))))
+    s.set_root(s.list([a, med]))
+    with pytest.raises(rtb.RtbError, match="boundary"):
+        s.flatten_stats()                           # a quad is not a closed boundary
+
+
+def test_bounds(rtb):
+    s = rtb.Scene(); m = s.lambertian(albedo=(1, 1, 1))
+    assert np.array_equal(s.bounds(s.sphere((1, 2, 3), 0.5, m)), np.float32([0.5, 1.5, 2.5, 1.5, 2.5, 3.5]))
+    assert np.array_equal(s.bounds(s.moving_sphere((0, 0, 0), (0, 1, 0), 1.0, m)), np.float32([-1, -1, -1, 1, 2, 1]))
+    b = s.bounds(s.quad((0, 0, 0), (2, 0, 0), (0, 3, 0), m))
+    assert np.allclose(b, [0, 0, -5e-5, 2, 3, 5e-5], atol=1e-9)
+    box = s.box((0, 0, 0), (2, 1, 4), m)
+    r = s.bounds(s.translate(s.rotate_y(box, 90.0), (10, 0, 0)))
+    assert np.allclose(r, [10, 0, -2, 14, 1, 0], atol=1e-4)
+    grp = s.list([box, s.sphere((5, 5, 5), 1.0, m)])
+    assert np.allclose(s.bounds(grp), [0, 0, 0, 6, 6, 6], atol=1e-4)
+
+
+def test_serialize_roundtrip_through_the_oracle_loader(rtb, orc):
+    for name in rtb.scene_names():
+        s = rtb.Scene.named(name)
+        blob = s.serialize()
+        h, mats, objs, children = parse_blob(blob)
+        assert h["magic"] == 0x53425452 and h["n_objects"] == s.num_objects() and 0 <= h["root_object"] < h["n_objects"]
+        assert orc.OracleScene(blob).handle
+
+
+def test_flattener(rtb):
+    stats = {n: rtb.Scene.named(n).flatten_stats() for n in rtb.scene_names()}
+    assert stats["book2_bouncing"] == {"primitives": 488, "record_slots": 488, "inner_nodes": 487, "depth": 10}
+    assert stats["book2_cornell"]["primitives"] == 18 and stats["book2_cornell"]["record_slots"] == 30      # 12 instanced quads take 2 slots
+    assert stats["book2_cornell_smoke"]["primitives"] == 6                                                   # two media live in the pre-test list
+    assert stats["book2_final"]["primitives"] == 400 * 6 + 1 + 4 + 2 + 1000                                  # boxes, light, spheres, textured, cluster
+    assert all(v["depth"] <= 30 for v in stats.values())
+    s = rtb.Scene(); s.set_root(s.sphere((0, 0, 0), 1.0, s.lambertian(albedo=(1, 1, 1))))
+    assert s.flatten_stats() == {"primitives": 1, "record_slots": 1, "inner_nodes": 0, "depth": 1}
+
+
+def test_host_mirror_scene_registry(rtb):
+    names = rtb.scene_names()
+    for n in ("book1_final", "book2_bouncing", "book2_checker", "book2_earth", "book2_perlin", "book2_cornell_smoke", "book2_final"):
+        assert n in names
+    s = rtb.Scene.named("book2_final"); i = s.info
+    assert (i.width, i.height, i.spp, i.max_depth) == (800, 800, 10000, 40)
+    s = rtb.Scene.named("book1_final"); i = s.info
+    assert (i.width, i.height, i.spp, i.max_depth, i.camera.kind) == (1200, 675, 10, 50, rtb.CAM_DEFOCUS)
+    with pytest.raises(rtb.RtbError):
+        rtb.Scene.named("no_such_scene")
+
+
+def test_cameras_follow_the_reference_constructors(rtb):
+    """cu_Cameras.cuh:15-25: w points forward, u = up x w, v = w x u, scaled by the viewport half extents."""
+    c = rtb.make_camera("pinhole", (0, 1, -4), (0, 1, 0), (0, 1, 0), 90.0, 16 / 9)
+    assert np.allclose(c.w[:], [0, 0, 1]) and np.allclose(c.u[:], [16 / 9, 0, 0], atol=1e-6) and np.allclose(c.v[:], [0, 1, 0], atol=1e-6)
+    d = rtb.make_camera("defocus", (13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 1.5, aperture=0.1, focus_dist=10.0)
+    assert abs(np.linalg.norm(d.u[:]) - 1) < 1e-6 and d.lens_radius == np.float32(0.05) and d.focus_dist == 10.0
+    m = rtb.make_camera("motion", (13, 2, 3), (0, 0, 0), (0, 1, 0), 30.0, 16 / 9, t0=0.1, t1=1.0)
+    assert m.kind == rtb.CAM_MOTION and m.t0 == np.float32(0.1) and m.t1 == 1.0

@@ -1,0 +1,212 @@
+"""CPU tests: the oracle pinned against the reference's own outputs (tests/golden/, produced by the
+reference's sources compiled unmodified — see tests/golden/make_golden.py) and against known answers."""
+import math
+import struct
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+from helpers import camera_rays, parse_blob, psnr, random_rays, tonemap
+
+
+# ---------------------------------------------------------------- arithmetic spec kernels
+
+def test_philox_known_answers(orc):
+    """Random123 kat_vectors for philox4x32-10."""
+    assert [hex(x) for x in orc.philox([0, 0, 0, 0], [0, 0])] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    assert [hex(x) for x in orc.philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2)] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    assert [hex(x) for x in orc.philox([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0])] == \
+        ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+
+
+def test_sincos_and_log_kernels(orc):
+    us = np.concatenate([np.linspace(1e-7, 1.0, 4001), [2.0 ** -33, 0.125, 0.25, 0.5, 0.75, 1.0]])
+    err = 0.0
+    for u in us:
+        s, c = orc.sincos2pi(float(np.float32(u)))
+        a = 2 * math.pi * float(np.float32(u))
+        err = max(err, abs(s - math.sin(a)), abs(c - math.cos(a)))
+    assert err < 5e-7
+    assert orc.sincos2pi(1.0) == (0.0, 1.0) and orc.sincos2pi(0.25) == (1.0, 0.0)
+    for x in np.geomspace(2.0 ** -33, 1.0, 2000):
+        x = float(np.float32(x))
+        assert abs(orc.logpos(x) - math.log(x)) <= 1e-6 * max(1.0, abs(math.log(x)))
+
+
+def test_xorwow_matches_device_curand(orc):
+    """curand_init(seed,0,0) + curand_uniform streams dumped on a B200 (oracle/_ref/ref_render rng)."""
+    d = np.fromfile(GOLDEN / "ref_rng.bin", dtype=np.float32)
+    dev = d[4608:].reshape(4, 64)
+    for i, seed in enumerate((1984, 1985, 1984 + 45000, 1984 + 89999)):
+        assert np.array_equal(orc.xorwow_uniforms(seed, 64), dev[i])
+    assert d[:4608].min() > 0.0 and d[:4608].max() <= 1.0      # (0,1]
+
+
+# ---------------------------------------------------------------- scene + BVH against the reference
+
+def test_scene_equals_reference_scene(rtb):
+    """The host mirror's SceneBook2BVH == what the reference's own Scenes.cu built (cuRAND stream, argument
+    evaluation order, sphere and material parameters), dumped from device memory on the GPU box."""
+    raw = np.fromfile(GOLDEN / "ref_scene_book2_bouncing.bin", dtype=np.uint8)
+    n = int(np.frombuffer(raw[:4], dtype=np.int32)[0])
+    rec = np.frombuffer(raw[4:], dtype=np.float32).reshape(n, 16)
+    s = rtb.Scene.named("book2_bouncing")
+    _, mats, objs, _ = parse_blob(s.serialize())
+    assert n == 488 and s.num_objects() == 489
+    kinds = {0: 0, 1: 0, 2: 0}
+    for i in range(n):
+        o, m = objs[i], mats[objs[i]["mat"]]
+        if rec[i, 0] == 1.0:
+            assert o["kind"] == 1 and np.array_equal(rec[i, 1:4], o["f"][:3]) and np.array_equal(rec[i, 4:7], o["f"][4:7]) and rec[i, 7] == o["f"][3]
+        else:
+            assert o["kind"] == 0 and np.array_equal(rec[i, 1:5], o["f"][:4])
+        assert np.array_equal(rec[i, 8:11], m["albedo"])
+        if m["kind"] in (1, 2):
+            assert rec[i, 11] == m["param"]
+        kinds[int(m["kind"])] += 1
+    assert kinds == {0: 396, 1: 63, 2: 29}      # 394 moving + ground + left; 62 + right; 28 + centre
+
+
+def _read_ref_bvh(path, rtb):
+    d = open(path, "rb").read()
+    nn, root = struct.unpack("ii", d[:8])
+    nodes = np.frombuffer(d[8:8 + 32 * nn], dtype=rtb.BVH_NODE_DTYPE)
+    order = np.frombuffer(d[8 + 32 * nn:], dtype=np.int32)
+    return nodes, order, root
+
+
+def test_bvh_bit_exact_vs_reference_golden(rtb, orc):
+    """Node array + primitive order of the reference's BuildBVH_TopDown (BVH.cu:166-210) on config 1/2's boxes."""
+    s = rtb.Scene.named("book2_bouncing")
+    boxes = np.array([s.bounds(i) for i in range(488)], dtype=np.float32)
+    gn, go, gr = _read_ref_bvh(GOLDEN / "ref_bvh_book2_bouncing.bin", rtb)
+    assert len(gn) == 975 and gr == 974 and gn[gr]["left_child_idx"] == 486 and gn[gr]["right_child_hittable_idx"] == 973
+    for build in (lambda: rtb.bvh_build(boxes, rtb.BVH_TOPDOWN_MEDIAN), lambda: orc.bvh_build(boxes, rtb.BVH_TOPDOWN_MEDIAN, rtb.BVH_NODE_DTYPE)):
+        n, o, r = build()
+        assert np.array_equal(n.view(np.uint8), gn.view(np.uint8)) and np.array_equal(o, go) and r == gr
+    # the world BVH the renderer traverses for this scene is that same tree
+    s.flatten_stats()
+    wn, wr = s.world_bvh()
+    assert np.array_equal(wn.view(np.uint8), gn.view(np.uint8)) and wr == gr
+
+
+@pytest.mark.skipif(not (ROOT / "oracle" / "_ref" / "ref_bvh").exists(), reason="reference-derived checker not built (needs /root/reference)")
+@pytest.mark.parametrize("builder,n", [(0, 3000), (0, 1), (0, 2), (0, 37), (2, 120)])
+def test_bvh_bit_exact_vs_reference_live(rtb, orc, builder, n, tmp_path):
+    """Random boxes with duplicate sort keys (the reference uses an unstable std::sort) through the reference's own BVH.cu."""
+    rng = np.random.default_rng(n + builder)
+    c = rng.uniform(-50, 50, (n, 3)).astype(np.float32); r = rng.uniform(0.1, 3, (n, 1)).astype(np.float32)
+    c[::3, 0] = np.round(c[::3, 0]); c[::5] = c[0]
+    boxes = np.concatenate([c - r, c + r], 1)
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    fin.write_bytes(struct.pack("i", n) + boxes.tobytes())
+    subprocess.run([str(ROOT / "oracle" / "_ref" / "ref_bvh"), str(fin), str(fout), str(builder)], check=True)
+    gn, go, gr = _read_ref_bvh(fout, rtb)
+    for got in (rtb.bvh_build(boxes, builder), orc.bvh_build(boxes, builder, rtb.BVH_NODE_DTYPE)):
+        assert np.array_equal(got[0].view(np.uint8), gn.view(np.uint8)) and np.array_equal(got[1], go) and got[2] == gr
+
+
+# ---------------------------------------------------------------- integrator against the reference megakernel
+
+def test_oracle_matches_reference_megakernel_per_pixel(rtb, orc):
+    """XORWOW mode = the reference's own streams: same image as render_kernel compiled for sm_100a, up to
+    paths whose branch flips on nvcc's FMA contraction (they also shift that pixel's stream)."""
+    ref = np.fromfile(GOLDEN / "ref_megakernel_200x112_4spp_d50.bin", dtype=np.float32).reshape(112, 200, 4)
+    s = rtb.Scene.named("book2_bouncing")
+    cam = rtb.make_camera("motion", (13, 2, 3), (0, 0, 0), (0, 1, 0), 30.0, 200 / 112.0, t0=0.1, t1=1.0)
+    osum, _, _ = orc.OracleScene(s.serialize()).render(cam, 200, 112, 0, 4, 50, seed=1984, mode=orc.RNG_XORWOW)
+    img = tonemap(osum)
+    assert np.array_equal(ref[..., 3], np.ones((112, 200), dtype=np.float32))
+    diff = np.abs(img - ref[..., :3]).max(axis=2)
+    assert (diff <= 1e-4).mean() > 0.95, f"only {(diff <= 1e-4).mean():.4f} of pixels agree to 1e-4"
+    assert psnr(img, ref[..., :3]) > 35.0
+
+
+def test_oracle_matches_reference_megakernel_config2(rtb, orc):
+    """Config 2 at full size (400x225, 100 spp, depth 50): PSNR and per-channel mean vs the reference's image."""
+    ref = np.load(GOLDEN / "ref_megakernel_400x225_100spp_d50_f16.npy").astype(np.float32)
+    s = rtb.Scene.named("book2_bouncing")
+    cam = s.info.camera
+    o = orc.OracleScene(s.serialize())
+    xs, _, _ = o.render(cam, 400, 225, 0, 100, 50, seed=1984, mode=orc.RNG_XORWOW)
+    assert psnr(tonemap(xs), ref) > 45.0
+    # the new path's own streams (Philox): a different sample set of the same estimator
+    ps, ps2, _ = o.render(cam, 400, 225, 0, 100, 50, seed=1984, mode=orc.RNG_PHILOX, want_sum2=True)
+    p = psnr(tonemap(ps), ref)
+    assert p > 30.0, f"PSNR {p:.1f} dB"
+    mean_p = (ps[..., :3] / 100.0); mean_x = (xs[..., :3] / 100.0)
+    var = np.maximum(ps2[..., :3] / 100.0 - mean_p ** 2, 0.0) / 100.0          # variance of each pixel mean
+    for c in range(3):
+        bias = float((mean_p[..., c] - mean_x[..., c]).mean())
+        sigma = float(np.sqrt(2.0 * var[..., c].sum()) / var[..., c].size)
+        assert abs(bias) <= 3.0 * sigma + 1e-4, f"channel {c}: mean error {bias:.2e} vs 3 sigma {3 * sigma:.2e}"
+
+
+# ---------------------------------------------------------------- oracle self-consistency / edge cases
+
+def test_traversal_order_does_not_change_hits(rtb, orc):
+    """Closest hit through the reference's BVH walk (BVH.cu:54-106) == linear HittableList scan == brute force index."""
+    src = rtb.Scene.named("book2_bouncing")
+    _, mats, objs, _ = parse_blob(src.serialize())
+    def build(kind):
+        s = rtb.Scene(); ids = []
+        for o in objs[:488]:
+            m = s.lambertian(albedo=(0.5, 0.5, 0.5))
+            ids.append(s.moving_sphere(o["f"][:3], o["f"][4:7], float(o["f"][3]), m) if o["kind"] == 1 else s.sphere(o["f"][:3], float(o["f"][3]), m))
+        s.set_root(s.bvh(ids) if kind == "bvh" else s.list(ids))
+        return s
+    rays = np.concatenate([camera_rays(rtb, src.info.camera, 160, 90, "renderer"), random_rays(rtb, 20000, -12, 12, seed=5)])
+    a = orc.OracleScene(build("bvh").serialize()).trace_rays(rays, rtb.HIT_DTYPE)
+    b = orc.OracleScene(build("list").serialize()).trace_rays(rays, rtb.HIT_DTYPE)
+    assert np.array_equal(a["object"], b["object"]) and np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32))
+    assert (a["object"] >= 0).sum() > 5000
+
+
+def test_sphere_index_recipe_cpu(rtb, orc):
+    """google_testing/test.cpp:87-106 recipe on the CPU side: brute force over raw spheres == oracle BVH trace."""
+    src = rtb.Scene.named("book2_bouncing")
+    _, _, objs, _ = parse_blob(src.serialize())
+    sp = np.array([[*o["f"][:3], o["f"][3]] for o in objs[:488]], dtype=np.float32)
+    W, H = 320, 180
+    cam = rtb.make_camera("pinhole", (0, 1, -4), (0, 1, 0), (0, 1, 0), 90.0, 1280 / 720)
+    truth = orc.sphere_index_image(sp, cam, W, H)
+    assert (truth >= 0).mean() > 0.5 and truth.max() < 488
+    s = rtb.Scene(); m = s.lambertian(albedo=(0.5, 0.5, 0.5))
+    s.set_root(s.bvh([s.sphere(c[:3], float(c[3]), m) for c in sp]))
+    hits = orc.OracleScene(s.serialize()).trace_rays(camera_rays(rtb, cam, W, H, "test"), rtb.HIT_DTYPE)
+    assert (hits["object"].reshape(H, W) == truth).mean() > 0.9999
+
+
+def test_medium_transmission_known_answer(rtb, orc):
+    """Beer-Lambert: an absorbing slab (isotropic albedo 0) of density s and thickness L in front of a white
+    background transmits exp(-s L)."""
+    s = rtb.Scene()
+    black = s.isotropic(s.solid((0, 0, 0)))
+    slab = s.box((-50, -50, 0), (50, 50, 4), s.lambertian(albedo=(1, 1, 1)))
+    s.set_root(s.list([s.constant_medium(slab, 0.25, black)]))
+    s.set_background(rtb.BG_CONSTANT, (1, 1, 1))
+    cam = rtb.make_camera("pinhole", (0, 0, -10), (0, 0, 0), (0, 1, 0), 2.0, 1.0)
+    acc, _, _ = orc.OracleScene(s.serialize()).render(cam, 32, 32, 0, 256, 8, seed=7)
+    mean = float((acc[..., 0] / acc[..., 3]).mean())
+    assert abs(mean - math.exp(-1.0)) < 0.004, mean
+
+
+def test_edge_cases(rtb, orc):
+    s = rtb.Scene.named("book2_checker")
+    o = orc.OracleScene(s.serialize())
+    cam = s.info.camera
+    acc, _, rays = o.render(cam, 8, 4, 5, 5, 10)                 # empty sample range
+    assert not acc.any() and rays == 0
+    acc, _, rays = o.render(cam, 1, 1, 0, 3, 1)                  # 1x1 image, a single segment per path
+    assert acc[0, 0, 3] == 3 and rays == 3
+    rays_in = np.zeros(4, dtype=rtb.RAY_DTYPE)                   # axis-aligned rays (zero direction components)
+    rays_in["o"] = [(0, 30, 0), (0, -30, 0), (50, 0, 0), (0, -10, 0)]
+    rays_in["d"] = [(0, -1, 0), (0, 1, 0), (0, 1, 0), (0, 1, 0)]
+    h = o.trace_rays(rays_in, rtb.HIT_DTYPE)
+    assert h["object"][0] >= 0 and h["object"][1] >= 0 and h["object"][2] == -1
+    assert h["t"][0] == 10.0 and h["t"][3] == 10.0               # from the centre of the lower sphere: near root < 0, far root taken
+    with pytest.raises(RuntimeError):
+        orc.OracleScene(b"not a scene")
