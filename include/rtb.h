@@ -105,6 +105,12 @@ int rtb_add_constant_medium(rtb_scene* s, int boundary, float density, int phase
 
 int rtb_scene_set_root(rtb_scene* s, int object);
 int rtb_scene_set_background(rtb_scene* s, int mode, const float rgb[3]);
+/* Which tree the renderer walks.  Closest hits do not depend on it (tests/test_gpu_parity.py checks that).
+ * RTB_WORLD_BVH_QUALITY (default): a binned-SAH tree over all flattened primitives.
+ * RTB_WORLD_BVH_AS_BUILT: when the scene root is a BVH, exactly the tree its BVH_Handle::Factory builder makes
+ * (same nodes, same primitive order as the reference), e.g. to inspect it with rtb_scene_world_bvh. */
+enum rtb_world_bvh_mode { RTB_WORLD_BVH_QUALITY = 0, RTB_WORLD_BVH_AS_BUILT = 1 };
+int rtb_scene_set_world_bvh(rtb_scene* s, int mode);
 
 int rtb_scene_num_objects(const rtb_scene* s);
 /* World-space bounds of an object: out6 = {min.xyz, max.xyz} (getSphereBounds & co). */
@@ -233,7 +239,9 @@ typedef struct rtb_hit {                                                        
 	float   n[3];         /* the normal materials see (spheres: outward; quads: facing the ray) */
 	int32_t front_face;   /* dot(d, geometric normal) <= 0 */
 	float   u, v;
-	int32_t pad[3];
+	int32_t nodes_visited;   /* traversal statistics of this ray (rtb_trace_rays only): inner nodes visited, */
+	int32_t prims_tested;    /* primitives intersected */
+	int32_t pad;
 } rtb_hit;
 
 /* Closest hits for n host rays through the traverse kernel (media are skipped: they are stochastic).

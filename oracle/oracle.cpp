@@ -366,7 +366,11 @@ struct Ctx {
 		}
 	}
 	float medium_u(int medium_index) {
-		if (mode == ORC_RNG_PHILOX) return rng4(seed, pixel, sample, bounce, STREAM_MEDIUM0 + (uint32_t)medium_index).x;
+		if (mode == ORC_RNG_PHILOX) {   // medium m: component (m & 3) of stream STREAM_MEDIUM0 + (m >> 2)
+			F4 q = rng4(seed, pixel, sample, bounce, STREAM_MEDIUM0 + ((uint32_t)medium_index >> 2));
+			int c = medium_index & 3;
+			return c == 0 ? q.x : (c == 1 ? q.y : (c == 2 ? q.z : q.w));
+		}
 		return xw->next();
 	}
 };

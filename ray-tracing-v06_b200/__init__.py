@@ -19,13 +19,14 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "librtb200.so"
+LIB_PATH = Path(os.environ["RTB_LIB"]) if os.environ.get("RTB_LIB") else _HERE / "librtb200.so"   # RTB_LIB: experimental builds only
 SCENES_LIB_PATH = _HERE / "librtb200_scenes.so"
 
 RTB_OK = 0
 TEX_SOLID, TEX_CHECKER, TEX_IMAGE, TEX_NOISE = 0, 1, 2, 3
 BVH_TOPDOWN_MEDIAN, BVH_TOPDOWN_SAH, BVH_BOTTOMUP = 0, 1, 2
 BG_SKY_GRADIENT, BG_CONSTANT = 0, 1
+WORLD_BVH_QUALITY, WORLD_BVH_AS_BUILT = 0, 1
 CAM_PINHOLE, CAM_DEFOCUS, CAM_MOTION = 0, 1, 2
 RENDER_CLEAR, RENDER_VARIANCE = 1, 2
 MISS_DIST = np.float32(3.402823466e38)
@@ -73,7 +74,7 @@ class SceneInfo(C.Structure):
 
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("time", np.float32), ("d", np.float32, 3), ("pad", np.float32)])
 HIT_DTYPE = np.dtype([("t", np.float32), ("prim", np.int32), ("object", np.int32), ("material", np.int32), ("p", np.float32, 3),
-                      ("n", np.float32, 3), ("front_face", np.int32), ("u", np.float32), ("v", np.float32), ("pad", np.int32, 3)])
+                      ("n", np.float32, 3), ("front_face", np.int32), ("u", np.float32), ("v", np.float32), ("nodes_visited", np.int32), ("prims_tested", np.int32), ("pad", np.int32)])
 BVH_NODE_DTYPE = np.dtype([("bmin", np.float32, 3), ("bmax", np.float32, 3), ("left_child_idx", np.int32), ("right_child_hittable_idx", np.int32)])
 assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 64 and BVH_NODE_DTYPE.itemsize == 32
 
@@ -107,6 +108,7 @@ ABI = {
     "rtb_add_constant_medium": (C.c_int, [_P, C.c_int, C.c_float, C.c_int]),
     "rtb_scene_set_root": (C.c_int, [_P, C.c_int]),
     "rtb_scene_set_background": (C.c_int, [_P, C.c_int, _F3]),
+    "rtb_scene_set_world_bvh": (C.c_int, [_P, C.c_int]),
     "rtb_scene_num_objects": (C.c_int, [_P]),
     "rtb_object_bounds": (C.c_int, [_P, C.c_int, _F3]),
     "rtb_scene_serialize": (C.c_size_t, [_P, _P, C.c_size_t]),
@@ -285,6 +287,7 @@ class Scene:
     def constant_medium(self, boundary, density, phase): return _check(lib().rtb_add_constant_medium(self.handle, boundary, density, phase), "rtb_add_constant_medium")
     def set_root(self, obj): _check(lib().rtb_scene_set_root(self.handle, obj), "rtb_scene_set_root")
     def set_background(self, mode, rgb=(0, 0, 0)): _check(lib().rtb_scene_set_background(self.handle, mode, _f3(rgb)), "rtb_scene_set_background")
+    def set_world_bvh(self, mode): _check(lib().rtb_scene_set_world_bvh(self.handle, mode), "rtb_scene_set_world_bvh")
     def num_objects(self): return lib().rtb_scene_num_objects(self.handle)
 
     def bounds(self, obj) -> np.ndarray:

@@ -144,30 +144,50 @@ __device__ __forceinline__ float planar_hit(v3 o, v3 d, const float4* pp, float4
 	return t;
 }
 
+// Free-flight uniforms of the media a ray meets.  Medium m of a path segment uses component (m & 3)
+// of Philox(seed, pixel; sample, bounce, STREAM_MEDIUM0 + (m >> 2)); the block is generated lazily,
+// only when some medium's boundary interval survives the geometric rejections, and shared by up to
+// four media.
+struct MediumRng {
+	uint32_t seed, pixel, sample, bounce;
+	uint32_t block;    // cached block index, 0xFFFFFFFF = none
+	rt::f4 u;
+	__device__ __forceinline__ float get(uint32_t m) {
+		const uint32_t b = m >> 2;
+		if (b != block) { u = rt::rng4(seed, pixel, sample, bounce, rt::STREAM_MEDIUM0 + b); block = b; }
+		const uint32_t c = m & 3u;
+		return c == 0 ? u.x : (c == 1 ? u.y : (c == 2 ? u.z : u.w));
+	}
+};
+__device__ __forceinline__ MediumRng make_medium_rng(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce) {
+	MediumRng r; r.seed = seed; r.pixel = pixel; r.sample = sample; r.bounce = bounce; r.block = 0xFFFFFFFFu;
+	r.u.x = r.u.y = r.u.z = r.u.w = 0.0f; return r;
+}
+
 // constant_medium::hit (book) over a convex boundary interval [t1,t2] found for any-sign t.
-__device__ __forceinline__ float medium_sample(float t1, float t2, float a, float neg_inv_density, float u, float tbest) {
+__device__ __forceinline__ float medium_sample(float t1, float t2, float a, float neg_inv_density, MediumRng& mr, uint32_t medium, float tbest) {
 	if (!(t2 > t1 + 0.0001f)) return FLT_MAX;     // second boundary query: interval(t1 + 0.0001, inf)
 	if (t1 < 0.0f) t1 = 0.0f;                     // ray_t.min (the reference accepts t >= 0)
 	if (t2 > tbest) t2 = tbest;                   // ray_t.max = closest so far
 	if (t1 >= t2) return FLT_MAX;
 	float len = sqrtf(a);
 	float dist_inside = (t2 - t1) * len;
-	float hit_distance = neg_inv_density * rt::logpos(u);
+	float hit_distance = neg_inv_density * rt::logpos(mr.get(medium));
 	if (hit_distance > dist_inside) return FLT_MAX;
 	return t1 + hit_distance / len;
 }
 
-__device__ __forceinline__ float medium_sphere_hit(v3 o, v3 d, float a, float4 q0, float nid, float u, float tbest) {
+__device__ __forceinline__ float medium_sphere_hit(v3 o, v3 d, float a, float4 q0, float nid, MediumRng& mr, uint32_t medium, float tbest) {
 	v3 oc = rt::sub(o, xyz(q0));
 	float hb = rt::dot(d, oc);
 	float cc = fmaf(-q0.w, q0.w, rt::dot(oc, oc));
 	float disc = fmaf(hb, hb, -(a * cc));
 	if (!(disc > 0.0f)) return FLT_MAX;
 	float sq = sqrtf(disc);
-	return medium_sample((-hb - sq) / a, (-hb + sq) / a, a, nid, u, tbest);
+	return medium_sample((-hb - sq) / a, (-hb + sq) / a, a, nid, mr, medium, tbest);
 }
 
-__device__ __forceinline__ float medium_box_hit(v3 o, v3 d, float a, float4 q0, float4 q1, float4 q2, float u, float tbest) {
+__device__ __forceinline__ float medium_box_hit(v3 o, v3 d, float a, float4 q0, float4 q1, float4 q2, MediumRng& mr, uint32_t medium, float tbest) {
 	// world -> object: translate back, rotate by -theta about y (book translate::hit / rotate_y::hit)
 	float cs = q0.w, sn = q1.w;
 	v3 ot = rt::sub(o, xyz(q2));
@@ -184,7 +204,7 @@ __device__ __forceinline__ float medium_box_hit(v3 o, v3 d, float a, float4 q0, 
 		tn = lo > tn ? lo : tn; tf = hi < tf ? hi : tf;
 	}
 	if (!(tn < tf)) return FLT_MAX;
-	return medium_sample(tn, tf, a, q2.w, u, tbest);
+	return medium_sample(tn, tf, a, q2.w, mr, medium, tbest);
 }
 
 // Instances.  T = (cos, sin, off.x, off.y), (off.z, -, -, -) with world = R_y(theta) * object + off.
@@ -208,11 +228,10 @@ __device__ __forceinline__ v3 xf_vec_to_world(const float4* tp, v3 v) {
 // ------------------------------------------------------------------------------------------------
 // traverse
 
-struct MediumRng { uint32_t seed, pixel, sample, bounce; };
 
 // One primitive against one ray: the t of the hit if it is closer than tbest, else FLT_MAX.
 template <bool MEDIA>
-__device__ __forceinline__ float leaf_test(const SceneView& sv, int code, v3 o, v3 d, float a, float time, const MediumRng& mr, float tbest) {
+__device__ __forceinline__ float leaf_test(const SceneView& sv, int code, v3 o, v3 d, float a, float time, MediumRng& mr, float tbest) {
 	const int type = code & 15;
 	const float4* pp = sv.prims + 4 * (size_t)(code >> RTB_LEAF_TYPE_BITS);
 	const float4 q0 = ldg4(pp);
@@ -237,22 +256,23 @@ __device__ __forceinline__ float leaf_test(const SceneView& sv, int code, v3 o, 
 	} else if (MEDIA) {
 		const float4 q1 = ldg4(pp + 1);
 		if (type == PRIM_MEDIUM_SPHERE) {
-			uint32_t mi = __float_as_uint(q1.y);
-			float u = rt::rng4(mr.seed, mr.pixel, mr.sample, mr.bounce, rt::STREAM_MEDIUM0 + mi).x;
-			t = medium_sphere_hit(o, d, a, q0, q1.x, u, tbest);
+			t = medium_sphere_hit(o, d, a, q0, q1.x, mr, __float_as_uint(q1.y), tbest);
 		} else {
 			const float4 q2 = ldg4(pp + 2), q3 = ldg4(pp + 3);
-			uint32_t mi = __float_as_uint(q3.x);
-			float u = rt::rng4(mr.seed, mr.pixel, mr.sample, mr.bounce, rt::STREAM_MEDIUM0 + mi).x;
-			t = medium_box_hit(o, d, a, q0, q1, q2, u, tbest);
+			t = medium_box_hit(o, d, a, q0, q1, q2, mr, __float_as_uint(q3.x), tbest);
 		}
 	}
 	return t;
 }
 
-template <bool MEDIA>
-__device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float time, const MediumRng& mr,
-                                          int* __restrict__ stack, float& tbest_out, int& code_out) {
+#ifndef TRAV_WHILE_WHILE
+#define TRAV_WHILE_WHILE 1
+#endif
+#define TRAV_END ((int)0x80000000)
+
+template <bool MEDIA, bool STATS = false>
+__device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float time, MediumRng& mr,
+                                          int* __restrict__ stack, float& tbest_out, int& code_out, int* stats_out = nullptr) {
 	const float a = rt::dot(d, d);
 	float tbest = FLT_MAX;
 	int best = -1;
@@ -268,16 +288,20 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 	const float gx = fabsf(d.x) < 1e-20f ? copysignf(1e-20f, d.x) : d.x;
 	const float gy = fabsf(d.y) < 1e-20f ? copysignf(1e-20f, d.y) : d.y;
 	const float gz = fabsf(d.z) < 1e-20f ? copysignf(1e-20f, d.z) : d.z;
-	const float idx = 1.0f / gx, idy = 1.0f / gy, idz = 1.0f / gz;
+	const float idx = __frcp_rn(gx), idy = __frcp_rn(gy), idz = __frcp_rn(gz);
 	const float oix = -(o.x * idx), oiy = -(o.y * idy), oiz = -(o.z * idz);
 
 	int cur = sv.root_ref;
 	int sp = 0;
+	int n_inner = 0, n_leaf = 0;   // STATS only
+	// "while-while" walk: lanes first descend inner nodes together, then test their leaf primitive
+	// together (a leaf reference is negative; TRAV_END marks an exhausted walk).
 	for (;;) {
-		if (cur >= 0) {
+		while (cur >= 0) {
+			if (STATS) ++n_inner;
 			const float4* np = sv.nodes + 4 * (size_t)cur;
 			const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2);
-			const int4 n3 = __ldg(reinterpret_cast<const int4*>(np + 3));
+			const int2 n3 = __ldg(reinterpret_cast<const int2*>(np + 3));
 			float lx0 = fmaf(n0.x, idx, oix), lx1 = fmaf(n0.w, idx, oix);
 			float ly0 = fmaf(n0.y, idy, oiy), ly1 = fmaf(n1.x, idy, oiy);
 			float lz0 = fmaf(n0.z, idz, oiz), lz1 = fmaf(n1.y, idz, oiz);
@@ -289,33 +313,42 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 			float rtmin = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fminf(rz0, rz1));
 			float rtmax = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fmaxf(rz0, rz1));
 			// aabb::intersects: tmin <= tmax && tmin < ray_max && tmax > 0   aabb.cuh:41
-			bool hl = ltmin <= ltmax && ltmin < tbest && ltmax > 0.0f;
-			bool hr = rtmin <= rtmax && rtmin < tbest && rtmax > 0.0f;
+			const bool hl = ltmin <= ltmax && ltmin < tbest && ltmax > 0.0f;
+			const bool hr = rtmin <= rtmax && rtmin < tbest && rtmax > 0.0f;
 			if (hl && hr) {
 				// nearer child next, farther child on the stack (BVH.cu:91-97); boxes that both contain
 				// the origin are ordered by where the ray leaves them
 				const float lk = fmaxf(ltmin, 0.0f), rk = fmaxf(rtmin, 0.0f);
-				bool sw = lk > rk || (lk == rk && ltmax > rtmax);
-				int nearc = sw ? n3.y : n3.x, farc = sw ? n3.x : n3.y;
-				stack[sp * TRAVERSE_THREADS] = farc; ++sp;
-				cur = nearc;
-				continue;
-			}
-			if (hl) { cur = n3.x; continue; }
-			if (hr) { cur = n3.y; continue; }
-		} else {
+				const bool sw = lk > rk || (lk == rk && ltmax > rtmax);
+				stack[sp * TRAVERSE_THREADS] = sw ? n3.x : n3.y; ++sp;
+				cur = sw ? n3.y : n3.x;
+			} else if (hl) cur = n3.x;
+			else if (hr) cur = n3.y;
+			else if (sp > 0) { --sp; cur = stack[sp * TRAVERSE_THREADS]; }
+			else cur = TRAV_END;
+#if !TRAV_WHILE_WHILE
+			break;   // if-if flavour: at most one inner node per trip
+#endif
+		}
+		if (cur == TRAV_END) break;
+		if (cur < 0) {
+			if (STATS) ++n_leaf;
 			const int code = ~cur;
 			const float t = leaf_test<MEDIA>(sv, code, o, d, a, time, mr, tbest);
 			if (t < tbest) { tbest = t; best = code; }   // "if (t >= rec.distance) return false"  SphereHittable.cu:58
+			if (sp == 0) break;
+			--sp; cur = stack[sp * TRAVERSE_THREADS];
 		}
-		if (sp == 0) break;
-		--sp; cur = stack[sp * TRAVERSE_THREADS];
 	}
+	if (STATS) { stats_out[0] = n_inner; stats_out[1] = n_leaf; }
 	tbest_out = tbest; code_out = best;
 }
 
+#ifndef TRAVERSE_MIN_BLOCKS
+#define TRAVERSE_MIN_BLOCKS 8   // 8 x 128 threads x 64 registers = the whole register file
+#endif
 template <bool MEDIA>
-__global__ void __launch_bounds__(TRAVERSE_THREADS)
+__global__ void __launch_bounds__(TRAVERSE_THREADS, TRAVERSE_MIN_BLOCKS)
 traverse_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
 	__shared__ int s_stack[STACK_SIZE * TRAVERSE_THREADS];
 	if (bounce >= *wv.tail_from) return;
@@ -335,11 +368,8 @@ traverse_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
 		const uint32_t i = base + lane;
 		if (i < n) {
 			const float4 fo = ro[i], fd = rd[i];
-			MediumRng mr{0, 0, 0, 0};
-			if (MEDIA) {
-				mr.seed = bp.seed; mr.bounce = bounce;
-				path_pixel_sample(bp, batch, __float_as_uint(fd.w), mr.pixel, mr.sample);
-			}
+			MediumRng mr = make_medium_rng(bp.seed, 0, 0, bounce);
+			if (MEDIA) path_pixel_sample(bp, batch, __float_as_uint(fd.w), mr.pixel, mr.sample);
 			float t; int code;
 			trace_ray<MEDIA>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code);
 			wv.hit[i] = make_int2(__float_as_int(t), code);
@@ -644,11 +674,11 @@ tail_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce0, uint32_
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
 		float4 fo = ro[i], fd = rd[i];
 		v3 thr = xyz(rt_[i]);
-		MediumRng mr{0, 0, 0, 0};
-		if (MEDIA) { mr.seed = bp.seed; path_pixel_sample(bp, batch, __float_as_uint(fd.w), mr.pixel, mr.sample); }
+		MediumRng mr = make_medium_rng(bp.seed, 0, 0, bounce0);
+		if (MEDIA) path_pixel_sample(bp, batch, __float_as_uint(fd.w), mr.pixel, mr.sample);
 		for (uint32_t b = bounce0; b < bp.max_depth; ++b) {
 			if (b > bounce0) ++extra;
-			mr.bounce = b;
+			mr.bounce = b; mr.block = 0xFFFFFFFFu;
 			float t; int code;
 			trace_ray<MEDIA>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code);
 			float4 no, nd; v3 nthr;
@@ -715,7 +745,7 @@ resolve_kernel(const float4* __restrict__ accum, float4* __restrict__ out, uint3
 
 __global__ void __launch_bounds__(TRAVERSE_THREADS)
 trace_rays_kernel(SceneView sv, const float4* __restrict__ ro, const float4* __restrict__ rd, uint32_t n,
-                  int2* __restrict__ hit, uint32_t* counter) {
+                  int2* __restrict__ hit, int2* __restrict__ stats, uint32_t* counter) {
 	__shared__ int s_stack[STACK_SIZE * TRAVERSE_THREADS];
 	const int lane = threadIdx.x & 31;
 	for (;;) {
@@ -726,10 +756,12 @@ trace_rays_kernel(SceneView sv, const float4* __restrict__ ro, const float4* __r
 		uint32_t i = base + lane;
 		if (i < n) {
 			float4 fo = ro[i], fd = rd[i];
-			MediumRng mr{0, 0, 0, 0};
+			MediumRng mr = make_medium_rng(0, 0, 0, 0);
 			float t; int code;
-			trace_ray<false>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code);
+			int st[2];
+			trace_ray<false, true>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code, st);
 			hit[i] = make_int2(__float_as_int(t), code);
+			stats[i] = make_int2(st[0], st[1]);
 		}
 		__syncwarp();
 	}
@@ -737,13 +769,13 @@ trace_rays_kernel(SceneView sv, const float4* __restrict__ ro, const float4* __r
 
 __global__ void __launch_bounds__(STREAM_THREADS)
 hit_record_kernel(SceneView sv, const float4* __restrict__ ro, const float4* __restrict__ rd, const int2* __restrict__ hit,
-                  uint32_t n, rtb_hit* __restrict__ out) {
+                  const int2* __restrict__ stats, uint32_t n, rtb_hit* __restrict__ out) {
 	const uint32_t stride = gridDim.x * blockDim.x;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
 		rtb_hit r;
 		const int2 h = hit[i];
 		r.t = __int_as_float(h.x);
-		r.pad[0] = r.pad[1] = r.pad[2] = 0;
+		r.nodes_visited = stats[i].x; r.prims_tested = stats[i].y; r.pad = 0;   // inner nodes visited, primitives tested
 		if (h.y < 0) {
 			r.t = FLT_MAX; r.prim = -1; r.object = -1; r.material = -1; r.front_face = 0; r.u = r.v = 0.0f;
 			r.p[0] = r.p[1] = r.p[2] = 0.0f; r.n[0] = r.n[1] = r.n[2] = 0.0f;
@@ -809,11 +841,11 @@ void launch_resolve(const float4* accum, float4* out, uint32_t n, cudaStream_t s
 	int blocks = (int)((n + STREAM_THREADS - 1) / STREAM_THREADS); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
 	resolve_kernel<<<blocks, STREAM_THREADS, 0, st>>>(accum, out, n);
 }
-void launch_trace_rays(const SceneView& sv, const float4* ray_o, const float4* ray_d, uint32_t n, int2* hit_tmp,
+void launch_trace_rays(const SceneView& sv, const float4* ray_o, const float4* ray_d, uint32_t n, int2* hit_tmp, int2* stats_tmp,
                        rtb_hit* hits_out, uint32_t* work_counter, const LaunchCfg& lc, cudaStream_t st) {
 	cudaMemsetAsync(work_counter, 0, sizeof(uint32_t), st);
-	trace_rays_kernel<<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, ray_o, ray_d, n, hit_tmp, work_counter);
-	hit_record_kernel<<<lc.blocks_stream, STREAM_THREADS, 0, st>>>(sv, ray_o, ray_d, hit_tmp, n, hits_out);
+	trace_rays_kernel<<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, ray_o, ray_d, n, hit_tmp, stats_tmp, work_counter);
+	hit_record_kernel<<<lc.blocks_stream, STREAM_THREADS, 0, st>>>(sv, ray_o, ray_d, hit_tmp, stats_tmp, n, hits_out);
 }
 
 }  // namespace rtb

@@ -63,7 +63,7 @@ void launch_accumulate(const BatchParams& bp, const WaveView& wv, float4* accum,
 void launch_resolve(const float4* accum, float4* out, uint32_t n, cudaStream_t st);
 
 // Parity hook: closest hits + full hit records for explicit rays (media skipped).
-void launch_trace_rays(const SceneView& sv, const float4* ray_o, const float4* ray_d, uint32_t n, int2* hit_tmp,
+void launch_trace_rays(const SceneView& sv, const float4* ray_o, const float4* ray_d, uint32_t n, int2* hit_tmp, int2* stats_tmp,
                        rtb_hit* hits_out, uint32_t* work_counter, const LaunchCfg& lc, cudaStream_t st);
 
 void query_occupancy(int device, LaunchCfg& lc);

@@ -432,18 +432,19 @@ int rtb_trace_rays(rtb_renderer* r, const rtb_ray* rays, size_t n, rtb_hit* hits
 		ho[i] = make_float4(rays[i].o[0], rays[i].o[1], rays[i].o[2], rays[i].time);
 		hd[i] = make_float4(rays[i].d[0], rays[i].d[1], rays[i].d[2], 0.0f);
 	}
-	float4 *d_o = nullptr, *d_d = nullptr; int2* d_hit = nullptr; rtb_hit* d_rec = nullptr; uint32_t* d_cnt = nullptr;
+	float4 *d_o = nullptr, *d_d = nullptr; int2 *d_hit = nullptr, *d_stats = nullptr; rtb_hit* d_rec = nullptr; uint32_t* d_cnt = nullptr;
 	int rc = RTB_OK;
-	auto cleanup = [&]() { cudaFree(d_o); cudaFree(d_d); cudaFree(d_hit); cudaFree(d_rec); cudaFree(d_cnt); };
+	auto cleanup = [&]() { cudaFree(d_o); cudaFree(d_d); cudaFree(d_hit); cudaFree(d_stats); cudaFree(d_rec); cudaFree(d_cnt); };
 #define TRY_OR_CLEAN(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(RTB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
 	TRY_OR_CLEAN(cudaMalloc(&d_o, n * 16));
 	TRY_OR_CLEAN(cudaMalloc(&d_d, n * 16));
 	TRY_OR_CLEAN(cudaMalloc(&d_hit, n * 8));
+	TRY_OR_CLEAN(cudaMalloc(&d_stats, n * 8));
 	TRY_OR_CLEAN(cudaMalloc(&d_rec, n * sizeof(rtb_hit)));
 	TRY_OR_CLEAN(cudaMalloc(&d_cnt, 256));
 	TRY_OR_CLEAN(cudaMemcpyAsync(d_o, ho.data(), n * 16, cudaMemcpyHostToDevice, r->stream));
 	TRY_OR_CLEAN(cudaMemcpyAsync(d_d, hd.data(), n * 16, cudaMemcpyHostToDevice, r->stream));
-	launch_trace_rays(r->sv, d_o, d_d, (uint32_t)n, d_hit, d_rec, d_cnt, r->lc, r->stream);
+	launch_trace_rays(r->sv, d_o, d_d, (uint32_t)n, d_hit, d_stats, d_rec, d_cnt, r->lc, r->stream);
 	r->launches += 2;
 	TRY_OR_CLEAN(cudaGetLastError());
 	TRY_OR_CLEAN(cudaMemcpyAsync(hits_out, d_rec, n * sizeof(rtb_hit), cudaMemcpyDeviceToHost, r->stream));

@@ -257,6 +257,10 @@ int rtb_scene_set_root(rtb_scene* s, int object) {
 	if (!s || !obj_ok(s, object)) return fail(RTB_ERR_INVALID, "rtb_scene_set_root: bad object id");
 	s->root = object; return RTB_OK;
 }
+int rtb_scene_set_world_bvh(rtb_scene* s, int mode) {
+	if (!s || (mode != RTB_WORLD_BVH_QUALITY && mode != RTB_WORLD_BVH_AS_BUILT)) return fail(RTB_ERR_INVALID, "rtb_scene_set_world_bvh: bad mode");
+	s->world_bvh_mode = mode; return RTB_OK;
+}
 int rtb_scene_set_background(rtb_scene* s, int mode, const float rgb[3]) {
 	if (!s || (mode != RTB_BG_SKY_GRADIENT && mode != RTB_BG_CONSTANT)) return fail(RTB_ERR_INVALID, "rtb_scene_set_background: bad mode");
 	s->background_mode = mode;
@@ -796,14 +800,15 @@ int flatten(rtb_scene& s, FlatScene& out) {
 		s.world_nodes.clear(); s.world_root = -1;
 	}
 
-	// World BVH.  A root that is a reference BVH keeps the reference's builder (and therefore its
-	// exact node / primitive order); anything else gets the quality SAH builder.
+	// World BVH: a quality SAH tree by default; with RTB_WORLD_BVH_AS_BUILT a root that is a reference BVH keeps the
+	// reference builder (and therefore its exact node / primitive order).  Closest hits are the same either way.
+
 	const rtbs_object& root = s.objects[s.root];
 	if (!out.bvh_empty) {
 	std::vector<rtb_bvh_node> nodes; std::vector<int> order; int root_idx = -1;
 	const int STACK_LIMIT = 30;
 	bool built = false;
-	if (root.kind == RTB_OBJ_BVH) {
+	if (root.kind == RTB_OBJ_BVH && s.world_bvh_mode == RTB_WORLD_BVH_AS_BUILT) {
 		rc = build_bvh(fl.prim_boxes, root.aux, nodes, order, root_idx);
 		if (rc < 0) return rc;
 		built = bvh_depth(nodes, root_idx) <= STACK_LIMIT;

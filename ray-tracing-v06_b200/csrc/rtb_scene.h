@@ -17,6 +17,7 @@ struct rtb_scene {
 	std::vector<uint8_t> blob;
 	int32_t root = -1;
 	int32_t background_mode = RTB_BG_SKY_GRADIENT;
+	int32_t world_bvh_mode = RTB_WORLD_BVH_QUALITY;
 	float background[3] = {0, 0, 0};
 
 	// Filled by flatten(): the world BVH in the reference's node layout (parity hook).

@@ -87,7 +87,8 @@ def test_bvh_bit_exact_vs_reference_golden(rtb, orc):
     for build in (lambda: rtb.bvh_build(boxes, rtb.BVH_TOPDOWN_MEDIAN), lambda: orc.bvh_build(boxes, rtb.BVH_TOPDOWN_MEDIAN, rtb.BVH_NODE_DTYPE)):
         n, o, r = build()
         assert np.array_equal(n.view(np.uint8), gn.view(np.uint8)) and np.array_equal(o, go) and r == gr
-    # the world BVH the renderer traverses for this scene is that same tree
+    # asked to walk the tree as built, the renderer traverses that same tree
+    s.set_world_bvh(rtb.WORLD_BVH_AS_BUILT)
     s.flatten_stats()
     wn, wr = s.world_bvh()
     assert np.array_equal(wn.view(np.uint8), gn.view(np.uint8)) and wr == gr

@@ -115,6 +115,25 @@ def test_hit_records_nested_instances(rtb, orc, renderer):
     assert np.array_equal(g["front_face"][hit], o["front_face"][hit]) or (g["front_face"][hit] != o["front_face"][hit]).mean() < 1e-4
 
 
+def test_world_bvh_choice_does_not_change_hits(rtb, renderer):
+    """The renderer walks a SAH tree by default; walking the tree exactly as the reference's builder made it
+    (RTB_WORLD_BVH_AS_BUILT) gives bit-identical hit records and images."""
+    rays = None; results = []
+    for mode in (rtb.WORLD_BVH_QUALITY, rtb.WORLD_BVH_AS_BUILT):
+        scene = rtb.Scene.named("book2_bouncing"); scene.set_world_bvh(mode)
+        renderer.set_scene(scene); renderer.set_camera(scene.info.camera)
+        if rays is None:
+            rays = np.concatenate([camera_rays(rtb, scene.info.camera, 320, 180, "renderer"), random_rays(rtb, 100_000, -12, 12, seed=2)])
+        h = renderer.trace_rays(rays)
+        renderer.render(160, 90, 0, 4, 50); img = renderer.download_accum()
+        results.append((h, img))
+    (h0, i0), (h1, i1) = results
+    for f in ("t", "object", "p", "n", "front_face"):
+        assert np.array_equal(h0[f], h1[f]), f
+    assert np.array_equal(i0, i1)
+    assert h1["nodes_visited"].mean() > 1.5 * h0["nodes_visited"].mean()    # and the SAH tree is the cheaper walk
+
+
 IMAGE_CASES = [
     # name, W, H, spp, depth, max mismatching pixel fraction
     ("book2_bouncing", 200, 112, 4, 50, 0.01),
