@@ -138,7 +138,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--spp-per-step", type=int, default=16, help="samples per pixel per GPU per step")
+    ap.add_argument("--spp-per-step", type=int, default=64, help="samples per pixel per GPU per step")
     ap.add_argument("--cpu-spp", type=int, default=8, help="samples per pixel of the cpu_baseline sample (rank 0, N=1)")
     ap.add_argument("--ref-spp", type=int, default=4, help="samples per pixel per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -165,7 +165,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"), timeout=datetime.timedelta(seconds=180))
 
     scene = pkg.Scene.named(SCENE)
     info = scene.info
@@ -231,7 +232,8 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         r.reset_counters(); r.set_profiling(True)
-        step(args.warmup + args.steps + e2e_steps)
+        s0p = ((args.warmup + args.steps + e2e_steps) * world + rank) * S
+        r.render(W, H, s0p, s0p + S, depth, seed=1984, clear=True, stream=stream)   # rank-local: no collective here
         prof = r.profile(); pc = r.counters(); r.set_profiling(False)
         total_ms = prof.generate_ms + prof.traverse_ms + prof.shade_ms + prof.accumulate_ms + prof.tail_ms
         ach = ALG_BYTES_PER_RAY_TRAVERSE * pc.rays / (prof.traverse_ms * 1e-3) / 1e9 if prof.traverse_ms > 0 else 0.0

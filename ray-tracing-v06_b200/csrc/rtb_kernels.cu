@@ -67,6 +67,7 @@ generate_kernel(BatchParams bp, rtb_camera cam, WaveView wv) {
 	if (blockIdx.x == 0) {
 		for (uint32_t i = threadIdx.x; i <= bp.max_depth; i += blockDim.x) wv.n_live[i] = (i == 0) ? n : 0u;
 		for (uint32_t i = threadIdx.x; i < 2 * (bp.max_depth + 1); i += blockDim.x) wv.work[i] = 0u;
+		for (uint32_t i = threadIdx.x; i <= bp.max_depth; i += blockDim.x) wv.n_tex[i] = 0u;
 		if (threadIdx.x == 0) *wv.tail_from = 0xFFFFFFFFu;
 	}
 
@@ -505,11 +506,21 @@ __device__ __forceinline__ bool texture_needs_uv(const SceneView& sv, int tex) {
 
 // Material::Scatter for every material kind.  Returns 0 = absorbed (path ends black),
 // 1 = scattered (dir/attenuation valid), 2 = emitted (attenuation holds the emitted radiance).
-__device__ __forceinline__ int scatter(const SceneView& sv, int mat, const Surface& s, v3 d, const rt::f4& r, v3& dir, v3& att) {
+// With DEFER, an image / noise albedo of a scattering material is not evaluated here: attenuation is
+// left at 1 and defer_tex names the texture, to be multiplied in later by texture_kernel (dense warps).
+template <bool DEFER>
+__device__ __forceinline__ int scatter(const SceneView& sv, int mat, const Surface& s, v3 d, const rt::f4& r, v3& dir, v3& att, int& defer_tex) {
 	const float4 m0 = ldg4(sv.materials + 2 * mat), m1 = ldg4(sv.materials + 2 * mat + 1);
 	const int kind = __float_as_int(m0.x), tex = __float_as_int(m0.y);
 	const float param = m0.z;
-	v3 albedo = tex >= 0 ? texture_value(sv, tex, s.u, s.v, s.p) : xyz(m1);
+	defer_tex = -1;
+	v3 albedo;
+	if (tex < 0) albedo = xyz(m1);
+	else {
+		const int tkind = __float_as_int(ldg4(sv.textures + 3 * tex).x);
+		if (DEFER && kind != RTB_MAT_DIFFUSE_LIGHT && (tkind == RTB_TEX_NOISE || tkind == RTB_TEX_IMAGE)) { defer_tex = tex; albedo = rt::mk(1.0f, 1.0f, 1.0f); }
+		else albedo = texture_value(sv, tex, s.u, s.v, s.p);
+	}
 	switch (kind) {
 	case RTB_MAT_LAMBERTIAN: {   // LambertianAbstract / LambertianTexture  cu_materials.cuh:26-40,52-64
 		dir = rt::add(s.n_shade, rt::unit_sphere(r.x, r.y));
@@ -567,9 +578,13 @@ __device__ __forceinline__ v3 background(const SceneView& sv, v3 d) {
 // Shades one traversed segment.  Returns true when the path continues (no/nd/nthr hold the scattered
 // ray and the updated throughput); otherwise the path has ended and its contribution (if any) has
 // been written to contrib[path].
+struct DeferredTex { int tex; float u, v; v3 p; };
+
+template <bool DEFER>
 __device__ __forceinline__ bool shade_segment(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t batch, uint32_t bounce,
                                               const float4& fo, const float4& fd, v3 thr, float t, int code,
-                                              float4& no, float4& nd, v3& nthr) {
+                                              float4& no, float4& nd, v3& nthr, DeferredTex& dt) {
+	dt.tex = -1;
 	const uint32_t path = __float_as_uint(fd.w);
 	const v3 o = xyz(fo), d = xyz(fd);
 	if (code < 0) {
@@ -585,13 +600,14 @@ __device__ __forceinline__ bool shade_segment(const SceneView& sv, const BatchPa
 	path_pixel_sample(bp, batch, path, pixel, sample);
 	const rt::f4 r = rt::rng4(bp.seed, pixel, sample, bounce, rt::STREAM_SCATTER);
 	v3 dir, att;
-	const int res = scatter(sv, info.x, s, d, r, dir, att);
+	const int res = scatter<DEFER>(sv, info.x, s, d, r, dir, att, dt.tex);
+	dt.u = s.u; dt.v = s.v; dt.p = s.p;
 	if (res == 2) {                                       // emitter: throughput * emitted, path ends
 		v3 c = rt::mulv(thr, att);
 		wv.contrib[path] = make_float4(c.x, c.y, c.z, 0.0f);
 		return false;
 	}
-	if (res != 1 || bounce + 1 >= bp.max_depth) return false;   // absorbed, or out of depth: black   Renderer.cu:164,180
+	if (res != 1 || bounce + 1 >= bp.max_depth) { dt.tex = -1; return false; }   // absorbed, or out of depth: black   Renderer.cu:164,180
 	// scatter_ray = Ray(at(t), dir, time); o += d * 0.001   Renderer.cu:168-175
 	v3 o2 = rt::madd(dir, 0.001f, s.p);
 	nthr = rt::mulv(thr, att);
@@ -625,10 +641,11 @@ shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
 		const uint32_t i = base + threadIdx.x;
 		bool alive = false;
 		float4 no = make_float4(0, 0, 0, 0), nd = no; v3 nthr = rt::mk(0, 0, 0);
+		DeferredTex dt; dt.tex = -1; dt.u = dt.v = 0.0f; dt.p = rt::mk(0, 0, 0);
 		if (i < n) {
 			const float4 fo = ro[i], fd = rd[i], ft = rt_[i];
 			const int2 h = wv.hit[i];
-			alive = shade_segment(sv, bp, wv, batch, bounce, fo, fd, xyz(ft), __int_as_float(h.x), h.y, no, nd, nthr);
+			alive = shade_segment<true>(sv, bp, wv, batch, bounce, fo, fd, xyz(ft), __int_as_float(h.x), h.y, no, nd, nthr, dt);
 		}
 		// live-path compaction: warp ballot/popc, one global atomic per block
 		const uint32_t mask = __ballot_sync(FULL_MASK, alive);
@@ -645,9 +662,45 @@ shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
 		if (alive) {
 			const uint32_t pos = s_base + s_warp[warp] + __popc(mask & ((1u << lane) - 1u));
 			wo[pos] = no; wd[pos] = nd; wt[pos] = make_float4(nthr.x, nthr.y, nthr.z, 0.0f);
+			// texture work list: (p, queue slot), (u, v, -, texture id)
+			const bool defer = dt.tex >= 0;
+			const uint32_t act = __activemask();
+			const uint32_t dmask = __ballot_sync(act, defer);
+			if (dmask) {
+				const int leader = __ffs(dmask) - 1;
+				uint32_t tb = 0;
+				if (lane == leader) tb = atomicAdd(wv.n_tex + bounce, (uint32_t)__popc(dmask));
+				tb = __shfl_sync(act, tb, leader);
+				if (defer) {
+					const uint32_t k = tb + __popc(dmask & ((1u << lane) - 1u));
+					wv.tex_work[2 * (size_t)k] = make_float4(dt.p.x, dt.p.y, dt.p.z, __uint_as_float(pos));
+					wv.tex_work[2 * (size_t)k + 1] = make_float4(dt.u, dt.v, 0.0f, __int_as_float(dt.tex));
+				}
+			}
 		}
 		base = s_chunk;
 		__syncthreads();
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// texture: evaluates the image / Perlin albedos that shade deferred, with dense warps, and folds them
+// into the throughput of the scattered rays (thr * value is the same single product either way).
+
+__global__ void __launch_bounds__(STREAM_THREADS)
+texture_kernel(SceneView sv, WaveView wv, uint32_t bounce) {
+	if (bounce >= *wv.tail_from) return;
+	const uint32_t n = wv.n_tex[bounce];
+	if (n == 0) return;
+	float4* __restrict__ wt = ((bounce & 1) ^ 1) ? wv.thr[1] : wv.thr[0];
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+		const float4 a = wv.tex_work[2 * (size_t)k], b = wv.tex_work[2 * (size_t)k + 1];
+		const v3 val = texture_value(sv, __float_as_int(b.w), b.x, b.y, xyz(a));
+		const uint32_t pos = __float_as_uint(a.w);
+		float4 t = wt[pos];
+		t.x *= val.x; t.y *= val.y; t.z *= val.z;
+		wt[pos] = t;
 	}
 }
 
@@ -682,7 +735,8 @@ tail_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce0, uint32_
 			float t; int code;
 			trace_ray<MEDIA>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code);
 			float4 no, nd; v3 nthr;
-			if (!shade_segment(sv, bp, wv, batch, b, fo, fd, thr, t, code, no, nd, nthr)) break;
+			DeferredTex dt;
+			if (!shade_segment<false>(sv, bp, wv, batch, b, fo, fd, thr, t, code, no, nd, nthr, dt)) break;
 			fo = no; fd = nd; thr = nthr;
 		}
 	}
@@ -832,6 +886,9 @@ void launch_tail(const SceneView& sv, const BatchParams& bp, const WaveView& wv,
 }
 void launch_shade(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st) {
 	shade_kernel<<<lc.blocks_shade, SHADE_THREADS, 0, st>>>(sv, bp, wv, bounce);
+}
+void launch_texture(const SceneView& sv, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st) {
+	texture_kernel<<<lc.blocks_stream, STREAM_THREADS, 0, st>>>(sv, wv, bounce);
 }
 void launch_accumulate(const BatchParams& bp, const WaveView& wv, float4* accum, float4* accum2, const LaunchCfg& lc, cudaStream_t st) {
 	accumulate_kernel<<<lc.blocks_stream, STREAM_THREADS, 0, st>>>(bp, wv, accum, accum2);

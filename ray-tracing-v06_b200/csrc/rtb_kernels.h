@@ -23,6 +23,7 @@ struct SceneView {
 	int32_t root_ref;
 	int32_t n_prims;
 	int32_t has_media;          // selects the traverse variant that draws free-flight distances
+	int32_t has_deferred_tex;   // some material has an image / noise albedo: texture_kernel is launched after shade
 	int32_t background_mode;
 	float bg_r, bg_g, bg_b;
 };
@@ -48,6 +49,8 @@ struct WaveView {
 	float4* contrib;            // per path: radiance carried by the terminated path
 	uint32_t* n_live;           // [max_depth + 1] queue lengths per bounce
 	uint32_t* work;             // [2 * (max_depth + 1)] dynamic work counters (traverse, shade)
+	float4* tex_work;           // deferred texture evaluations: 2 x float4 per entry
+	uint32_t* n_tex;            // [max_depth + 1] entries per bounce
 	uint32_t* batch_index;      // device-side batch counter (graph replays need no new arguments)
 	uint32_t* tail_from;        // first bounce handled by the fused tail kernel (0xFFFFFFFF: none yet)
 	unsigned long long* totals; // [0] paths, [1] rays
@@ -59,6 +62,7 @@ void launch_generate(const BatchParams& bp, const rtb_camera& cam, const WaveVie
 void launch_traverse(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st);
 void launch_tail(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, uint32_t threshold, const LaunchCfg& lc, cudaStream_t st);
 void launch_shade(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st);
+void launch_texture(const SceneView& sv, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st);
 void launch_accumulate(const BatchParams& bp, const WaveView& wv, float4* accum, float4* accum2, const LaunchCfg& lc, cudaStream_t st);
 void launch_resolve(const float4* accum, float4* out, uint32_t n, cudaStream_t st);
 

@@ -172,6 +172,11 @@ int rtb_renderer_set_scene(rtb_renderer* r, rtb_scene* s) {
 	r->sv.root_ref = fs.root_ref;
 	r->sv.n_prims = (int32_t)fs.prims.size();
 	r->sv.has_media = fs.n_media > 0;
+	r->sv.has_deferred_tex = 0;
+	for (size_t i = 0; i < fs.materials.size(); ++i) {
+		const DevMaterial& m = fs.materials[i];
+		if (m.tex >= 0 && m.kind != RTB_MAT_DIFFUSE_LIGHT && (fs.textures[m.tex].kind == RTB_TEX_NOISE || fs.textures[m.tex].kind == RTB_TEX_IMAGE)) r->sv.has_deferred_tex = 1;
+	}
 	r->sv.background_mode = fs.background_mode;
 	r->sv.bg_r = fs.background[0]; r->sv.bg_g = fs.background[1]; r->sv.bg_b = fs.background[2];
 	r->has_scene = true;
@@ -217,6 +222,7 @@ static int ensure_wave(rtb_renderer* r, size_t paths, uint32_t depth) {
 	size_t o_ro0 = take(P * 16), o_ro1 = take(P * 16), o_rd0 = take(P * 16), o_rd1 = take(P * 16);
 	size_t o_t0 = take(P * 16), o_t1 = take(P * 16), o_hit = take(P * 8), o_con = take(P * 16);
 	size_t o_live = take((depth + 2) * 4), o_work = take(2 * (depth + 2) * 4), o_batch = take(256), o_tot = take(256);
+	size_t o_tex = take(P * 32), o_ntex = take((depth + 2) * 4);
 	CUDA_TRY(cudaMalloc(&r->d_wave, off));
 	CUDA_TRY(cudaMemset(r->d_wave, 0, off));
 	uint8_t* b = static_cast<uint8_t*>(r->d_wave);
@@ -225,6 +231,7 @@ static int ensure_wave(rtb_renderer* r, size_t paths, uint32_t depth) {
 	r->wv.thr[0] = (float4*)(b + o_t0); r->wv.thr[1] = (float4*)(b + o_t1);
 	r->wv.hit = (int2*)(b + o_hit); r->wv.contrib = (float4*)(b + o_con);
 	r->wv.n_live = (uint32_t*)(b + o_live); r->wv.work = (uint32_t*)(b + o_work);
+	r->wv.tex_work = (float4*)(b + o_tex); r->wv.n_tex = (uint32_t*)(b + o_ntex);
 	r->wv.batch_index = (uint32_t*)(b + o_batch); r->wv.tail_from = r->wv.batch_index + 1; r->wv.totals = (unsigned long long*)(b + o_tot);
 	r->wave_paths = P; r->wave_depth = depth;
 	return RTB_OK;
@@ -243,7 +250,9 @@ static void enqueue_batch(rtb_renderer* r, const BatchParams& bp, cudaStream_t s
 	for (uint32_t b = 0; b < bp.max_depth; ++b) {
 		if (r->tail_threshold && tail_checkpoint(b)) { prof_begin(r, 4, st); launch_tail(r->sv, bp, r->wv, b, r->tail_threshold, r->lc, st); prof_end(r, st); }
 		prof_begin(r, 1, st); launch_traverse(r->sv, bp, r->wv, b, r->lc, st); prof_end(r, st);
-		prof_begin(r, 2, st); launch_shade(r->sv, bp, r->wv, b, r->lc, st); prof_end(r, st);
+		prof_begin(r, 2, st); launch_shade(r->sv, bp, r->wv, b, r->lc, st);
+		if (r->sv.has_deferred_tex && b + 1 < bp.max_depth) launch_texture(r->sv, r->wv, b, r->lc, st);
+		prof_end(r, st);
 	}
 	prof_begin(r, 3, st); launch_accumulate(bp, r->wv, r->d_accum, r->d_accum2, r->lc, st); prof_end(r, st);
 }
@@ -294,7 +303,8 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 	CUDA_TRY(cudaEventRecord(r->ev_t0, st));
 
 	const uint32_t n_batches = spp ? (uint32_t)((spp + S - 1) / S) : 0;
-	const uint64_t launches_per_batch = 3 + 2ull * bp.max_depth + (r->tail_threshold ? count_tail_checkpoints(bp.max_depth) : 0);
+	const uint64_t launches_per_batch = 3 + 2ull * bp.max_depth + (r->tail_threshold ? count_tail_checkpoints(bp.max_depth) : 0) +
+	                                    (r->sv.has_deferred_tex ? bp.max_depth - 1 : 0);
 	const bool use_graph = getenv("RTB_NO_GRAPH") == nullptr && n_batches > 0 && !r->profiling;
 	if (use_graph) {
 		bool reuse = r->graph_valid && memcmp(&r->graph_bp, &bp, sizeof bp) == 0 && memcmp(&r->graph_cam, &r->cam, sizeof r->cam) == 0 &&
