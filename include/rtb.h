@@ -225,6 +225,8 @@ typedef struct rtb_profile {
 int  rtb_renderer_set_profiling(rtb_renderer* r, int on);
 int  rtb_get_profile(rtb_renderer* r, rtb_profile* out);   /* synchronizes; totals since the last call */
 int  rtb_reset_counters(rtb_renderer* r);
+/* Live-queue length at every bounce of the LAST batch rendered (out[b], b < cap); returns max_depth. */
+int  rtb_queue_lengths(rtb_renderer* r, uint32_t* out, int cap);
 
 /* ------------------------------------------------------------------ hit-record parity hook */
 

@@ -133,6 +133,7 @@ ABI = {
     "rtb_download_accum": (C.c_int, [_P, _P, _P]),
     "rtb_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "rtb_reset_counters": (C.c_int, [_P]),
+    "rtb_queue_lengths": (C.c_int, [_P, _P, C.c_int]),
     "rtb_renderer_set_profiling": (C.c_int, [_P, C.c_int]),
     "rtb_get_profile": (C.c_int, [_P, C.POINTER(Profile)]),
     "rtb_trace_rays": (C.c_int, [_P, _P, C.c_size_t, _P]),
@@ -374,6 +375,11 @@ class Renderer:
         c = Counters()
         _check(lib().rtb_get_counters(self.handle, C.byref(c)), "rtb_get_counters")
         return c
+
+    def queue_lengths(self, cap: int = 256) -> np.ndarray:
+        out = np.zeros(cap, dtype=np.uint32)
+        n = _check(lib().rtb_queue_lengths(self.handle, out.ctypes.data, cap), "rtb_queue_lengths")
+        return out[:min(n, cap)]
 
     def set_profiling(self, on: bool):
         _check(lib().rtb_renderer_set_profiling(self.handle, 1 if on else 0), "rtb_renderer_set_profiling")

@@ -422,6 +422,16 @@ int rtb_get_profile(rtb_renderer* r, rtb_profile* out) {
 	return RTB_OK;
 }
 
+int rtb_queue_lengths(rtb_renderer* r, uint32_t* out, int cap) {
+	if (!r || !out || cap <= 0) return fail(RTB_ERR_INVALID, "rtb_queue_lengths: bad argument");
+	if (!r->d_wave) return fail(RTB_ERR_STATE, "rtb_queue_lengths: nothing rendered");
+	CUDA_TRY(cudaSetDevice(r->device));
+	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	int n = (int)r->wave_depth < cap ? (int)r->wave_depth : cap;
+	CUDA_TRY(cudaMemcpy(out, r->wv.n_live, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	return (int)r->wave_depth;
+}
+
 int rtb_reset_counters(rtb_renderer* r) {
 	if (!r) return fail(RTB_ERR_INVALID, "rtb_reset_counters: null renderer");
 	CUDA_TRY(cudaSetDevice(r->device));
