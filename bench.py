@@ -237,7 +237,14 @@ def main():
         prof = r.profile(); pc = r.counters(); r.set_profiling(False)
         total_ms = prof.generate_ms + prof.traverse_ms + prof.shade_ms + prof.accumulate_ms + prof.tail_ms
         ach = ALG_BYTES_PER_RAY_TRAVERSE * pc.rays / (prof.traverse_ms * 1e-3) / 1e9 if prof.traverse_ms > 0 else 0.0
-        roof = {"bound": "hbm", "kernel": "traverse_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        traffic = None
+        try:   # DRAM bytes per ray of the kernel from the committed ncu --set full capture, scaled to this run's rays per launch
+            tj = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())["traverse_kernel"]
+            traffic = tj["dram_bytes_per_ray"] * pc.rays / max(1, prof.traverse_launches)
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": "traverse_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_note": "bytes per launch = 47.4 B/ray (dram__bytes_read+write of profiles/r1_traverse_ncu.txt) x rays per launch; algorithmic 40 B/ray",
                 "peak_source": peak_src, "algorithmic_bytes_per_ray": ALG_BYTES_PER_RAY_TRAVERSE,
                 "avg_launch_ms": prof.traverse_ms / max(1, prof.traverse_launches), "launches": int(prof.traverse_launches),
                 "note": "traversal is FP32-issue/latency bound (scene is L1/L2 resident); HBM carries only the wavefront queues"}

@@ -888,7 +888,8 @@ void launch_shade(const SceneView& sv, const BatchParams& bp, const WaveView& wv
 	shade_kernel<<<lc.blocks_shade, SHADE_THREADS, 0, st>>>(sv, bp, wv, bounce);
 }
 void launch_texture(const SceneView& sv, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st) {
-	texture_kernel<<<lc.blocks_stream, STREAM_THREADS, 0, st>>>(sv, wv, bounce);
+	const int blocks = lc.sms * 2 < lc.blocks_stream ? lc.sms * 2 : lc.blocks_stream;   // short work lists: a small grid keeps the launch cheap
+	texture_kernel<<<blocks, STREAM_THREADS, 0, st>>>(sv, wv, bounce);
 }
 void launch_accumulate(const BatchParams& bp, const WaveView& wv, float4* accum, float4* accum2, const LaunchCfg& lc, cudaStream_t st) {
 	accumulate_kernel<<<lc.blocks_stream, STREAM_THREADS, 0, st>>>(bp, wv, accum, accum2);
