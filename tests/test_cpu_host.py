@@ -123,3 +123,11 @@ def test_cameras_follow_the_reference_constructors(rtb):
     assert abs(np.linalg.norm(d.u[:]) - 1) < 1e-6 and d.lens_radius == np.float32(0.05) and d.focus_dist == 10.0
     m = rtb.make_camera("motion", (13, 2, 3), (0, 0, 0), (0, 1, 0), 30.0, 16 / 9, t0=0.1, t1=1.0)
     assert m.kind == rtb.CAM_MOTION and m.t0 == np.float32(0.1) and m.t1 == 1.0
+
+
+def test_cli_app_builds_and_lists_scenes(rtb):
+    import subprocess
+    app = ROOT / "ray-tracing-v06_b200" / "rtb_app"
+    assert app.exists(), "run __graft_entry__.build()"
+    out = subprocess.run([str(app), "--list"], capture_output=True, text=True, check=True).stdout.split()
+    assert out == rtb.scene_names()

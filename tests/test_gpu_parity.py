@@ -208,3 +208,25 @@ def test_errors_are_loud(rtb):
         r.set_scene(s)                      # no root
     with pytest.raises(rtb.RtbError):
         s.sphere((0, 0, 0), 1.0, 5)         # bad material id
+
+
+def test_cli_app_matches_the_library(rtb, renderer, tmp_path):
+    """rtb_app book2_bouncing goes through the host mirror exactly like FirstApp::MakeApp/Run
+    (MotionBlurCamera -> SceneBook2BVH::Factory -> Renderer::MakeRenderer -> Render -> DownloadRenderbuffer)
+    and writes the 8-bit image the way write_renderbuffer does (x*255.999, rows flipped)."""
+    import subprocess
+    from conftest import ROOT
+    out = tmp_path / "img.ppm"
+    W, H, SPP, D = 160, 90, 4, 12
+    subprocess.run([str(ROOT / "ray-tracing-v06_b200" / "rtb_app"), "book2_bouncing", "--width", str(W), "--height", str(H), "--spp", str(SPP),
+                    "--depth", str(D), "--out", str(out)], check=True, capture_output=True)
+    raw = out.read_bytes()
+    header = f"P6\n{W} {H}\n255\n".encode()
+    assert raw.startswith(header)
+    img = np.frombuffer(raw[len(header):], dtype=np.uint8).reshape(H, W, 3)
+    scene = rtb.Scene.named("book2_bouncing")
+    cam = rtb.make_camera("motion", (13, 2, 3), (0, 0, 0), (0, 1, 0), 30.0, W / H, t0=0.1, t1=1.0)
+    renderer.set_scene(scene); renderer.set_camera(cam)
+    renderer.render(W, H, 0, SPP, D, seed=1984)
+    ref = (renderer.download()[::-1, :, :3] * np.float32(255.999)).astype(np.uint8)
+    assert np.array_equal(img, ref)
