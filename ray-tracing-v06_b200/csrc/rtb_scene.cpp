@@ -855,8 +855,18 @@ int flatten(rtb_scene& s, FlatScene& out) {
 			const rtb_bvh_node& l = nodes[nodes[i].left_child_idx];
 			const rtb_bvh_node& r = nodes[nodes[i].right_child_hittable_idx];
 			DevNode& d = out.nodes[dev_index[i]];
-			d.f[0] = l.bmin[0]; d.f[1] = l.bmin[1]; d.f[2] = l.bmin[2]; d.f[3] = l.bmax[0]; d.f[4] = l.bmax[1]; d.f[5] = l.bmax[2];
-			d.f[6] = r.bmin[0]; d.f[7] = r.bmin[1]; d.f[8] = r.bmin[2]; d.f[9] = r.bmax[0]; d.f[10] = r.bmax[1]; d.f[11] = r.bmax[2];
+			// each child box as (min, extent): the kernel forms both slab planes with FMAs, near/far chosen by
+			// the ray's direction signs.  The extent is rounded up (and min + extent >= max re-checked) so the
+			// box the kernel sees always contains the exact one.
+			auto put_box = [](float* f, const rtb_bvh_node& b) {
+				for (int k = 0; k < 3; ++k) {
+					float mn = b.bmin[k], ext = (b.bmax[k] - mn) * 1.000001f;
+					if (!(ext >= 0.0f)) ext = 0.0f;
+					while (mn + ext < b.bmax[k]) ext = std::nextafter(ext * 1.000001f + 1e-30f, INFINITY);
+					f[k] = mn; f[3 + k] = ext;
+				}
+			};
+			put_box(d.f, l); put_box(d.f + 6, r);
 			d.left = ref_of(nodes[i].left_child_idx); d.right = ref_of(nodes[i].right_child_hittable_idx); d.pad0 = d.pad1 = 0;
 		}
 		out.root_ref = 0;

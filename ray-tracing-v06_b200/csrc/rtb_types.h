@@ -23,9 +23,10 @@ enum PrimType : int {
 // ~ref = (prim_index << 4) | PrimType.
 inline int make_leaf_ref(int prim, int type) { return ~((prim << RTB_LEAF_TYPE_BITS) | type); }
 
-// 64-byte inner node holding BOTH children's boxes, fetched as 4 x LDG.128:
-//   a = (l.min.x, l.min.y, l.min.z, l.max.x)   b = (l.max.y, l.max.z, r.min.x, r.min.y)
-//   c = (r.min.z, r.max.x, r.max.y, r.max.z)   d = (left ref, right ref, 0, 0) as int bits
+// 64-byte inner node holding BOTH children's boxes as (min, extent), fetched as 4 x LDG.128:
+//   a = (l.min.x, l.min.y, l.min.z, l.ext.x)   b = (l.ext.y, l.ext.z, r.min.x, r.min.y)
+//   c = (r.min.z, r.ext.x, r.ext.y, r.ext.z)   d = (left ref, right ref, 0, 0) as int bits
+// extents are rounded up so min + ext >= max: the box the kernel tests contains the exact one.
 struct alignas(64) DevNode { float f[12]; int32_t left, right, pad0, pad1; };
 
 // 64-byte primitive record (4 x float4):
