@@ -33,6 +33,10 @@ struct rtb_renderer {
 	// scene arena
 	void* d_scene = nullptr; size_t scene_bytes = 0, scene_upload_bytes = 0;
 	SceneView sv{};
+	std::vector<uint8_t> staging;           // host copy of the arena of the last flattened scene
+	size_t off[7] = {0, 0, 0, 0, 0, 0, 0};
+	SceneView staged_sv{};
+	uint64_t staged_uid = 0, staged_version = 0;
 	bool has_scene = false;
 	uint64_t scene_version = 0;
 	rtb_camera cam{};
@@ -131,57 +135,67 @@ void rtb_renderer_destroy(rtb_renderer* r) {
 
 int rtb_renderer_set_scene(rtb_renderer* r, rtb_scene* s) {
 	if (!r || !s) return fail(RTB_ERR_INVALID, "rtb_renderer_set_scene: null argument");
-	FlatScene fs;
-	int rc = flatten(*s, fs);
-	if (rc) return rc;
 	CUDA_TRY(cudaSetDevice(r->device));
+	// An unchanged scene (same object, same version) is not flattened again: only the arena is re-sent.
+	const bool cached = r->staged_uid == s->uid && r->staged_version == s->version && !r->staging.empty();
+	if (!cached) {
+		FlatScene fs;
+		int rc = flatten(*s, fs);
+		if (rc) return rc;
+		// one arena, every section 256-byte aligned
+		size_t off_nodes = 0;
+		size_t off_prims = align_up(off_nodes + fs.nodes.size() * sizeof(DevNode), 256);
+		size_t off_info = align_up(off_prims + fs.prims.size() * sizeof(DevPrim), 256);
+		size_t off_mats = align_up(off_info + fs.prim_info.size() * sizeof(DevPrimInfo), 256);
+		size_t off_texs = align_up(off_mats + fs.materials.size() * sizeof(DevMaterial), 256);
+		size_t off_blob = align_up(off_texs + fs.textures.size() * sizeof(DevTexture), 256);
+		size_t off_pre = align_up(off_blob + fs.blob.size(), 256);
+		size_t total = align_up(off_pre + fs.pre_list.size() * 4, 256) + 256;
+		r->staging.assign(total, 0);
+		uint8_t* st = r->staging.data();
+		if (!fs.nodes.empty()) memcpy(st + off_nodes, fs.nodes.data(), fs.nodes.size() * sizeof(DevNode));
+		memcpy(st + off_prims, fs.prims.data(), fs.prims.size() * sizeof(DevPrim));
+		memcpy(st + off_info, fs.prim_info.data(), fs.prim_info.size() * sizeof(DevPrimInfo));
+		if (!fs.materials.empty()) memcpy(st + off_mats, fs.materials.data(), fs.materials.size() * sizeof(DevMaterial));
+		if (!fs.textures.empty()) memcpy(st + off_texs, fs.textures.data(), fs.textures.size() * sizeof(DevTexture));
+		if (!fs.blob.empty()) memcpy(st + off_blob, fs.blob.data(), fs.blob.size());
+		if (!fs.pre_list.empty()) memcpy(st + off_pre, fs.pre_list.data(), fs.pre_list.size() * 4);
+		r->off[0] = off_nodes; r->off[1] = off_prims; r->off[2] = off_info; r->off[3] = off_mats; r->off[4] = off_texs; r->off[5] = off_blob; r->off[6] = off_pre;
+		r->staged_sv = SceneView{};
+		r->staged_sv.root_ref = fs.root_ref;
+		r->staged_sv.n_prims = (int32_t)fs.prims.size();
+		r->staged_sv.n_pre = (int32_t)fs.pre_list.size();
+		r->staged_sv.bvh_empty = fs.bvh_empty;
+		r->staged_sv.has_media = fs.n_media > 0;
+		r->staged_sv.has_deferred_tex = 0;
+		for (size_t i = 0; i < fs.materials.size(); ++i) {
+			const DevMaterial& m = fs.materials[i];
+			if (m.tex >= 0 && m.kind != RTB_MAT_DIFFUSE_LIGHT && (fs.textures[m.tex].kind == RTB_TEX_NOISE || fs.textures[m.tex].kind == RTB_TEX_IMAGE)) r->staged_sv.has_deferred_tex = 1;
+		}
+		r->staged_sv.background_mode = fs.background_mode;
+		r->staged_sv.bg_r = fs.background[0]; r->staged_sv.bg_g = fs.background[1]; r->staged_sv.bg_b = fs.background[2];
+		r->staged_uid = s->uid; r->staged_version = s->version;
+	}
+	const size_t total = r->staging.size();
 	CUDA_TRY(cudaStreamSynchronize(r->stream));
-	// one arena, every section 256-byte aligned
-	size_t off_nodes = 0;
-	size_t off_prims = align_up(off_nodes + fs.nodes.size() * sizeof(DevNode), 256);
-	size_t off_info = align_up(off_prims + fs.prims.size() * sizeof(DevPrim), 256);
-	size_t off_mats = align_up(off_info + fs.prim_info.size() * sizeof(DevPrimInfo), 256);
-	size_t off_texs = align_up(off_mats + fs.materials.size() * sizeof(DevMaterial), 256);
-	size_t off_blob = align_up(off_texs + fs.textures.size() * sizeof(DevTexture), 256);
-	size_t off_pre = align_up(off_blob + fs.blob.size(), 256);
-	size_t total = align_up(off_pre + fs.pre_list.size() * 4, 256) + 256;
-	std::vector<uint8_t> staging(total, 0);
-	if (!fs.nodes.empty()) memcpy(staging.data() + off_nodes, fs.nodes.data(), fs.nodes.size() * sizeof(DevNode));
-	memcpy(staging.data() + off_prims, fs.prims.data(), fs.prims.size() * sizeof(DevPrim));
-	memcpy(staging.data() + off_info, fs.prim_info.data(), fs.prim_info.size() * sizeof(DevPrimInfo));
-	if (!fs.materials.empty()) memcpy(staging.data() + off_mats, fs.materials.data(), fs.materials.size() * sizeof(DevMaterial));
-	if (!fs.textures.empty()) memcpy(staging.data() + off_texs, fs.textures.data(), fs.textures.size() * sizeof(DevTexture));
-	if (!fs.blob.empty()) memcpy(staging.data() + off_blob, fs.blob.data(), fs.blob.size());
-	if (!fs.pre_list.empty()) memcpy(staging.data() + off_pre, fs.pre_list.data(), fs.pre_list.size() * 4);
 	if (total > r->scene_bytes) {
 		cudaFree(r->d_scene); r->d_scene = nullptr; r->scene_bytes = 0;
 		CUDA_TRY(cudaMalloc(&r->d_scene, total));
 		r->scene_bytes = total;
 	}
-	CUDA_TRY(cudaMemcpy(r->d_scene, staging.data(), total, cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMemcpy(r->d_scene, r->staging.data(), total, cudaMemcpyHostToDevice));
 	uint8_t* base = static_cast<uint8_t*>(r->d_scene);
-	r->sv.nodes = reinterpret_cast<const float4*>(base + off_nodes);
-	r->sv.prims = reinterpret_cast<const float4*>(base + off_prims);
-	r->sv.prim_info = reinterpret_cast<const int2*>(base + off_info);
-	r->sv.materials = reinterpret_cast<const float4*>(base + off_mats);
-	r->sv.textures = reinterpret_cast<const float4*>(base + off_texs);
-	r->sv.blob = base + off_blob;
-	r->sv.pre_list = reinterpret_cast<const int32_t*>(base + off_pre);
-	r->sv.n_pre = (int32_t)fs.pre_list.size();
-	r->sv.bvh_empty = fs.bvh_empty;
-	r->sv.root_ref = fs.root_ref;
-	r->sv.n_prims = (int32_t)fs.prims.size();
-	r->sv.has_media = fs.n_media > 0;
-	r->sv.has_deferred_tex = 0;
-	for (size_t i = 0; i < fs.materials.size(); ++i) {
-		const DevMaterial& m = fs.materials[i];
-		if (m.tex >= 0 && m.kind != RTB_MAT_DIFFUSE_LIGHT && (fs.textures[m.tex].kind == RTB_TEX_NOISE || fs.textures[m.tex].kind == RTB_TEX_IMAGE)) r->sv.has_deferred_tex = 1;
-	}
-	r->sv.background_mode = fs.background_mode;
-	r->sv.bg_r = fs.background[0]; r->sv.bg_g = fs.background[1]; r->sv.bg_b = fs.background[2];
+	r->sv = r->staged_sv;
+	r->sv.nodes = reinterpret_cast<const float4*>(base + r->off[0]);
+	r->sv.prims = reinterpret_cast<const float4*>(base + r->off[1]);
+	r->sv.prim_info = reinterpret_cast<const int2*>(base + r->off[2]);
+	r->sv.materials = reinterpret_cast<const float4*>(base + r->off[3]);
+	r->sv.textures = reinterpret_cast<const float4*>(base + r->off[4]);
+	r->sv.blob = base + r->off[5];
+	r->sv.pre_list = reinterpret_cast<const int32_t*>(base + r->off[6]);
 	r->has_scene = true;
 	r->scene_upload_bytes = total;
-	r->scene_version++;
+	if (!cached) r->scene_version++;   // same bytes at the same addresses: the cached graph stays valid
 	return RTB_OK;
 }
 

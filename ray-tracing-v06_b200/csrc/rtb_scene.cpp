@@ -10,6 +10,7 @@
 #include "rtb_scene.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -87,7 +88,9 @@ const char* rtb_last_error(void) { return g_last_error.c_str(); }
 
 int rtb_scene_create(rtb_scene** out) {
 	if (!out) return fail(RTB_ERR_INVALID, "rtb_scene_create: null out");
+	static std::atomic<uint64_t> next_uid{1};
 	*out = new rtb_scene();
+	(*out)->uid = next_uid.fetch_add(1);
 	return RTB_OK;
 }
 void rtb_scene_destroy(rtb_scene* s) { delete s; }
@@ -96,7 +99,7 @@ static bool tex_ok(const rtb_scene* s, int t) { return t >= 0 && t < (int)s->tex
 static bool mat_ok(const rtb_scene* s, int m) { return m >= 0 && m < (int)s->materials.size(); }
 static bool obj_ok(const rtb_scene* s, int o) { return o >= 0 && o < (int)s->objects.size(); }
 
-static int push_texture(rtb_scene* s, const rtbs_texture& t) { s->textures.push_back(t); return (int)s->textures.size() - 1; }
+static int push_texture(rtb_scene* s, const rtbs_texture& t) { s->version++; s->textures.push_back(t); return (int)s->textures.size() - 1; }
 
 int rtb_add_solid_texture(rtb_scene* s, const float rgb[3]) {
 	if (!s || !rgb) return fail(RTB_ERR_INVALID, "rtb_add_solid_texture: null argument");
@@ -158,7 +161,7 @@ int rtb_add_noise_texture(rtb_scene* s, float scale, uint32_t seed) {
 static int push_material(rtb_scene* s, int kind, int tex, const float a[3], float param) {
 	rtbs_material m{}; m.kind = kind; m.tex = tex; m.param = param;
 	m.albedo[0] = a ? a[0] : 1.0f; m.albedo[1] = a ? a[1] : 1.0f; m.albedo[2] = a ? a[2] : 1.0f;
-	s->materials.push_back(m); return (int)s->materials.size() - 1;
+	s->version++; s->materials.push_back(m); return (int)s->materials.size() - 1;
 }
 int rtb_add_lambertian(rtb_scene* s, int tex) {
 	if (!s || !tex_ok(s, tex)) return fail(RTB_ERR_INVALID, "rtb_add_lambertian: bad texture id");
@@ -185,7 +188,7 @@ int rtb_add_isotropic(rtb_scene* s, int tex) {
 	return push_material(s, RTB_MAT_ISOTROPIC, tex, nullptr, 0.0f);
 }
 
-static int push_object(rtb_scene* s, const rtbs_object& o) { s->objects.push_back(o); return (int)s->objects.size() - 1; }
+static int push_object(rtb_scene* s, const rtbs_object& o) { s->version++; s->objects.push_back(o); return (int)s->objects.size() - 1; }
 static rtbs_object blank_object(int kind, int mat) {
 	rtbs_object o{}; o.kind = kind; o.mat = mat; o.child_begin = 0; o.child_count = 0; o.aux = 0; return o;
 }
@@ -255,15 +258,15 @@ int rtb_add_constant_medium(rtb_scene* s, int boundary, float density, int phase
 }
 int rtb_scene_set_root(rtb_scene* s, int object) {
 	if (!s || !obj_ok(s, object)) return fail(RTB_ERR_INVALID, "rtb_scene_set_root: bad object id");
-	s->root = object; return RTB_OK;
+	s->root = object; s->version++; return RTB_OK;
 }
 int rtb_scene_set_world_bvh(rtb_scene* s, int mode) {
 	if (!s || (mode != RTB_WORLD_BVH_QUALITY && mode != RTB_WORLD_BVH_AS_BUILT)) return fail(RTB_ERR_INVALID, "rtb_scene_set_world_bvh: bad mode");
-	s->world_bvh_mode = mode; return RTB_OK;
+	s->world_bvh_mode = mode; s->version++; return RTB_OK;
 }
 int rtb_scene_set_background(rtb_scene* s, int mode, const float rgb[3]) {
 	if (!s || (mode != RTB_BG_SKY_GRADIENT && mode != RTB_BG_CONSTANT)) return fail(RTB_ERR_INVALID, "rtb_scene_set_background: bad mode");
-	s->background_mode = mode;
+	s->background_mode = mode; s->version++;
 	if (rgb) { s->background[0] = rgb[0]; s->background[1] = rgb[1]; s->background[2] = rgb[2]; }
 	return RTB_OK;
 }

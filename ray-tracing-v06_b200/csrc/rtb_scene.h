@@ -18,6 +18,8 @@ struct rtb_scene {
 	int32_t root = -1;
 	int32_t background_mode = RTB_BG_SKY_GRADIENT;
 	int32_t world_bvh_mode = RTB_WORLD_BVH_QUALITY;
+	uint64_t uid = 0;       // unique per rtb_scene_create
+	uint64_t version = 0;   // bumped by every mutating call: lets a renderer skip re-flattening an unchanged scene
 	float background[3] = {0, 0, 0};
 
 	// Filled by flatten(): the world BVH in the reference's node layout (parity hook).
