@@ -246,8 +246,8 @@ typedef struct rtb_hit {                                                        
 	int32_t pad;
 } rtb_hit;
 
-/* Closest hits for n host rays through the traverse kernel (media are skipped: they are stochastic).
- * seed/sample/bounce only matter when include_media != 0. */
+/* Closest hits for n host rays through the traversal code of the wavefront (media are skipped: they are
+ * stochastic), with the full hit record materials would see and per-ray traversal statistics. */
 int rtb_trace_rays(rtb_renderer* r, const rtb_ray* rays, size_t n, rtb_hit* hits_out);
 
 #ifdef __cplusplus
