@@ -131,3 +131,16 @@ def test_cli_app_builds_and_lists_scenes(rtb):
     assert app.exists(), "run __graft_entry__.build()"
     out = subprocess.run([str(app), "--list"], capture_output=True, text=True, check=True).stdout.split()
     assert out == rtb.scene_names()
+
+
+def test_world_bvh_depth_is_bounded_for_degenerate_input(rtb):
+    """The traverse kernel's per-thread stack holds 32 entries; the flattener must never hand it a deeper tree."""
+    s = rtb.Scene(); m = s.lambertian(albedo=(1, 1, 1))
+    same = [s.sphere((1, 2, 3), 0.5, m) for _ in range(3000)]            # 3000 coincident primitives: no split plane exists
+    s.set_root(s.list(same))
+    st = s.flatten_stats()
+    assert st["primitives"] == 3000 and st["depth"] <= 30
+    s2 = rtb.Scene(); m2 = s2.lambertian(albedo=(1, 1, 1))
+    line = [s2.sphere((float(2 ** (k % 60)), 0, 0), 1e-3 * (k + 1), m2) for k in range(120)]   # bottom-up merge builds a long chain here
+    s2.set_root(s2.bvh(line, rtb.BVH_BOTTOMUP)); s2.set_world_bvh(rtb.WORLD_BVH_AS_BUILT)
+    assert s2.flatten_stats()["depth"] <= 30
