@@ -144,3 +144,16 @@ def test_world_bvh_depth_is_bounded_for_degenerate_input(rtb):
     line = [s2.sphere((float(2 ** (k % 60)), 0, 0), 1e-3 * (k + 1), m2) for k in range(120)]   # bottom-up merge builds a long chain here
     s2.set_root(s2.bvh(line, rtb.BVH_BOTTOMUP)); s2.set_world_bvh(rtb.WORLD_BVH_AS_BUILT)
     assert s2.flatten_stats()["depth"] <= 30
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU restatement on the host cores) must print one JSON line with the agreed keys."""
+    import json, subprocess, sys
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-spp", "1"],
+                         capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    line = json.loads(out[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "cpu_baseline", "gpu_launches"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["vs_baseline"] is None
