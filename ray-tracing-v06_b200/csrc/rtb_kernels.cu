@@ -25,7 +25,9 @@ using rt::v3;
 #define TRAVERSE_THREADS 128
 #define SHADE_THREADS 256
 #define STREAM_THREADS 256
+#ifndef STACK_SIZE
 #define STACK_SIZE 32
+#endif
 #define FULL_MASK 0xFFFFFFFFu
 
 // ------------------------------------------------------------------------------------------------
@@ -350,10 +352,12 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 #ifndef TRAVERSE_MIN_BLOCKS
 #define TRAVERSE_MIN_BLOCKS 8   // 8 x 128 threads x 64 registers = the whole register file
 #endif
-template <bool MEDIA>
+// STACK = entries of the per-thread stack in shared memory: 16 when the tree is shallow enough (8 KB per
+// block instead of 16 KB leaves 64 KB more L1 per SM: -2 % on the Book 2 final scene), 32 otherwise.
+template <bool MEDIA, int STACK>
 __global__ void __launch_bounds__(TRAVERSE_THREADS, TRAVERSE_MIN_BLOCKS)
 traverse_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
-	__shared__ int s_stack[STACK_SIZE * TRAVERSE_THREADS];
+	__shared__ int s_stack[STACK * TRAVERSE_THREADS];
 	if (bounce >= *wv.tail_from) return;
 	const uint32_t n = wv.n_live[bounce];
 	if (n == 0) return;
@@ -858,8 +862,8 @@ void query_occupancy(int device, LaunchCfg& lc) {
 	cudaGetDeviceProperties(&prop, device);
 	int sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
 	int occ_t = 0, occ_tm = 0, occ_s = 0, occ_g = 0;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, traverse_kernel<false>, TRAVERSE_THREADS, 0);
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tm, traverse_kernel<true>, TRAVERSE_THREADS, 0);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, traverse_kernel<false, STACK_SIZE>, TRAVERSE_THREADS, 0);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tm, traverse_kernel<true, STACK_SIZE>, TRAVERSE_THREADS, 0);
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, shade_kernel, SHADE_THREADS, 0);
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, generate_kernel, STREAM_THREADS, 0);
 	int occ_trav = occ_t < occ_tm ? occ_t : occ_tm;
@@ -879,8 +883,14 @@ void launch_generate(const BatchParams& bp, const rtb_camera& cam, const WaveVie
 }
 void launch_traverse(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st) {
 	// media need the per-path RNG inside traversal; scenes without media skip that code entirely
-	if (sv.has_media) traverse_kernel<true><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce);
-	else traverse_kernel<false><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce);
+	const bool small = sv.tree_depth <= 17;   // a walk keeps at most depth - 1 entries on its stack
+	if (sv.has_media) {
+		if (small) traverse_kernel<true, 16><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce);
+		else traverse_kernel<true, STACK_SIZE><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce);
+	} else {
+		if (small) traverse_kernel<false, 16><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce);
+		else traverse_kernel<false, STACK_SIZE><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce);
+	}
 }
 void launch_tail(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, uint32_t threshold, const LaunchCfg& lc, cudaStream_t st) {
 	if (sv.has_media) tail_kernel<true><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, threshold);

@@ -22,6 +22,7 @@ struct SceneView {
 	int32_t bvh_empty;
 	int32_t root_ref;
 	int32_t n_prims;
+	int32_t tree_depth;         // depth of the world BVH in nodes (selects the stack size of the traverse kernel)
 	int32_t has_media;          // selects the traverse variant that draws free-flight distances
 	int32_t has_deferred_tex;   // some material has an image / noise albedo: texture_kernel is launched after shade
 	int32_t background_mode;

@@ -164,6 +164,7 @@ int rtb_renderer_set_scene(rtb_renderer* r, rtb_scene* s) {
 		r->staged_sv = SceneView{};
 		r->staged_sv.root_ref = fs.root_ref;
 		r->staged_sv.n_prims = (int32_t)fs.prims.size();
+		r->staged_sv.tree_depth = fs.max_depth_nodes;
 		r->staged_sv.n_pre = (int32_t)fs.pre_list.size();
 		r->staged_sv.bvh_empty = fs.bvh_empty;
 		r->staged_sv.has_media = fs.n_media > 0;

@@ -1,6 +1,7 @@
 #!/bin/bash
 # Runs bench.py once per experimental library under ray-tracing-v06_b200/variants (see tools/build_variant.sh).
 mkdir -p gpurun_out
+shopt -s nullglob
 for lib in "" ray-tracing-v06_b200/variants/*.so; do
   name=$(basename "${lib:-default}" .so)
   RTB_LIB=${lib:+$PWD/$lib} python bench.py --steps 5 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/sweep_$name.json 2>/dev/null
