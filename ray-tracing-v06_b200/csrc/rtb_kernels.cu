@@ -273,7 +273,9 @@ __device__ __forceinline__ float leaf_test(const SceneView& sv, int code, v3 o, 
 #endif
 #define TRAV_END ((int)0x80000000)
 
-template <bool MEDIA, bool STATS = false>
+// MEDIA: 0 = the scene has no media; 1 = all of them are in the pre-test list (the walk itself never meets
+// one: no RNG state is carried through the loop); 2 = more than the list holds, the rest are BVH leaves.
+template <int MEDIA, bool STATS = false>
 __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float time, MediumRng& mr,
                                           int* __restrict__ stack, float& tbest_out, int& code_out, int* stats_out = nullptr) {
 	const float a = rt::dot(d, d);
@@ -339,7 +341,7 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 		if (cur < 0) {
 			if (STATS) ++n_leaf;
 			const int code = ~cur;
-			const float t = leaf_test<MEDIA>(sv, code, o, d, a, time, mr, tbest);
+			const float t = leaf_test<(MEDIA == 2)>(sv, code, o, d, a, time, mr, tbest);
 			if (t < tbest) { tbest = t; best = code; }   // "if (t >= rec.distance) return false"  SphereHittable.cu:58
 			if (sp == 0) break;
 			--sp; cur = stack[sp * TRAVERSE_THREADS];
@@ -354,7 +356,7 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 #endif
 // STACK = entries of the per-thread stack in shared memory: 16 when the tree is shallow enough (8 KB per
 // block instead of 16 KB leaves 64 KB more L1 per SM: -2 % on the Book 2 final scene), 32 otherwise.
-template <bool MEDIA, int STACK>
+template <int MEDIA, int STACK>
 __global__ void __launch_bounds__(TRAVERSE_THREADS, TRAVERSE_MIN_BLOCKS)
 traverse_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
 	__shared__ int s_stack[STACK * TRAVERSE_THREADS];
@@ -739,7 +741,7 @@ tail_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce0, uint32_
 			if (b > bounce0) ++extra;
 			mr.bounce = b; mr.block = 0xFFFFFFFFu;
 			float t; int code;
-			trace_ray<MEDIA>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code);
+			trace_ray<(MEDIA ? 2 : 0)>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code);
 			float4 no, nd; v3 nthr;
 			DeferredTex dt;
 			if (!shade_segment<false>(sv, bp, wv, batch, b, fo, fd, thr, t, code, no, nd, nthr, dt)) break;
@@ -819,7 +821,7 @@ trace_rays_kernel(SceneView sv, const float4* __restrict__ ro, const float4* __r
 			MediumRng mr = make_medium_rng(0, 0, 0, 0);
 			float t; int code;
 			int st[2];
-			trace_ray<false, true>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code, st);
+			trace_ray<0, true>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code, st);
 			hit[i] = make_int2(__float_as_int(t), code);
 			stats[i] = make_int2(st[0], st[1]);
 		}
@@ -862,8 +864,8 @@ void query_occupancy(int device, LaunchCfg& lc) {
 	cudaGetDeviceProperties(&prop, device);
 	int sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
 	int occ_t = 0, occ_tm = 0, occ_s = 0, occ_g = 0;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, traverse_kernel<false, STACK_SIZE>, TRAVERSE_THREADS, 0);
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tm, traverse_kernel<true, STACK_SIZE>, TRAVERSE_THREADS, 0);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, traverse_kernel<0, STACK_SIZE>, TRAVERSE_THREADS, 0);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tm, traverse_kernel<2, STACK_SIZE>, TRAVERSE_THREADS, 0);
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, shade_kernel, SHADE_THREADS, 0);
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, generate_kernel, STREAM_THREADS, 0);
 	int occ_trav = occ_t < occ_tm ? occ_t : occ_tm;
@@ -884,13 +886,13 @@ void launch_generate(const BatchParams& bp, const rtb_camera& cam, const WaveVie
 void launch_traverse(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st) {
 	// media need the per-path RNG inside traversal; scenes without media skip that code entirely
 	const bool small = sv.tree_depth <= 17;   // a walk keeps at most depth - 1 entries on its stack
-	if (sv.has_media) {
-		if (small) traverse_kernel<true, 16><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce);
-		else traverse_kernel<true, STACK_SIZE><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce);
-	} else {
-		if (small) traverse_kernel<false, 16><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce);
-		else traverse_kernel<false, STACK_SIZE><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce);
-	}
+#define RTB_LAUNCH_TRAVERSE(M) \
+	do { if (small) traverse_kernel<M, 16><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce); \
+	     else traverse_kernel<M, STACK_SIZE><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce); } while (0)
+	if (sv.has_media == 0) RTB_LAUNCH_TRAVERSE(0);
+	else if (sv.has_media == 1) RTB_LAUNCH_TRAVERSE(1);
+	else RTB_LAUNCH_TRAVERSE(2);
+#undef RTB_LAUNCH_TRAVERSE
 }
 void launch_tail(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, uint32_t threshold, const LaunchCfg& lc, cudaStream_t st) {
 	if (sv.has_media) tail_kernel<true><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, threshold);

@@ -23,7 +23,7 @@ struct SceneView {
 	int32_t root_ref;
 	int32_t n_prims;
 	int32_t tree_depth;         // depth of the world BVH in nodes (selects the stack size of the traverse kernel)
-	int32_t has_media;          // selects the traverse variant that draws free-flight distances
+	int32_t has_media;          // 0 none, 1 all media in the pre-test list, 2 some media are BVH leaves (selects the traverse variant)
 	int32_t has_deferred_tex;   // some material has an image / noise albedo: texture_kernel is launched after shade
 	int32_t background_mode;
 	float bg_r, bg_g, bg_b;

@@ -167,7 +167,7 @@ int rtb_renderer_set_scene(rtb_renderer* r, rtb_scene* s) {
 		r->staged_sv.tree_depth = fs.max_depth_nodes;
 		r->staged_sv.n_pre = (int32_t)fs.pre_list.size();
 		r->staged_sv.bvh_empty = fs.bvh_empty;
-		r->staged_sv.has_media = fs.n_media > 0;
+		r->staged_sv.has_media = fs.n_media == 0 ? 0 : (fs.n_media <= (int32_t)fs.pre_list.size() ? 1 : 2);
 		r->staged_sv.has_deferred_tex = 0;
 		for (size_t i = 0; i < fs.materials.size(); ++i) {
 			const DevMaterial& m = fs.materials[i];
