@@ -288,7 +288,7 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 
 	const uint32_t spp = p->sample_end - p->sample_begin;
 	const uint64_t npix = (uint64_t)p->width * (row_end - row_begin);
-	uint64_t target_paths = 16ull << 20;
+	uint64_t target_paths = 64ull << 20;   // ~9.7 GB of queues; larger batches keep late, thin bounces full (RTB_BATCH_PATHS overrides)
 	if (const char* e = getenv("RTB_BATCH_PATHS")) { uint64_t v = strtoull(e, nullptr, 10); if (v > 0) target_paths = v; }
 	uint64_t S = p->samples_per_batch ? p->samples_per_batch : target_paths / npix;
 	if (S < 1) S = 1;
