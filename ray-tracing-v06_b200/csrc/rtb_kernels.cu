@@ -22,7 +22,9 @@ namespace rtb {
 
 using rt::v3;
 
+#ifndef TRAVERSE_THREADS
 #define TRAVERSE_THREADS 128
+#endif
 #define SHADE_THREADS 256
 #define STREAM_THREADS 256
 #ifndef STACK_SIZE
