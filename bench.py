@@ -139,8 +139,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spp-per-step", type=int, default=100, help="samples per pixel per GPU per step")
-    ap.add_argument("--cpu-spp", type=int, default=8, help="samples per pixel of the cpu_baseline sample (rank 0, N=1)")
-    ap.add_argument("--ref-spp", type=int, default=4, help="samples per pixel per step of the --impl reference arm")
+    ap.add_argument("--cpu-spp", type=int, default=128, help="samples per pixel of the cpu_baseline sample (rank 0, N=1)")
+    ap.add_argument("--ref-spp", type=int, default=16, help="samples per pixel per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
