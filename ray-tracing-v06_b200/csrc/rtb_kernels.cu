@@ -220,6 +220,7 @@ __device__ __forceinline__ void xf_ray(const float4* tp, v3 o, v3 d, v3& oo, v3&
 	const float4 t0 = ldg4(tp), t1 = ldg4(tp + 1);
 	const float cs = t0.x, sn = t0.y;
 	const v3 ot = rt::sub(o, rt::mk(t0.z, t0.w, t1.x));
+	if (t1.y == 0.0f) { oo = ot; dd = d; return; }   // translate only: the book's translate::hit leaves the direction alone (signed zeros included)
 	oo = rt::mk(fmaf(cs, ot.x, -(sn * ot.z)), ot.y, fmaf(sn, ot.x, cs * ot.z));
 	dd = rt::mk(fmaf(cs, d.x, -(sn * d.z)), d.y, fmaf(sn, d.x, cs * d.z));
 }
@@ -227,6 +228,7 @@ __device__ __forceinline__ void xf_ray(const float4* tp, v3 o, v3 d, v3& oo, v3&
 __device__ __forceinline__ v3 xf_vec_to_world(const float4* tp, v3 v) {
 	const float4 t0 = ldg4(tp);
 	const float cs = t0.x, sn = t0.y;
+	if (ldg4(tp + 1).y == 0.0f) return v;   // translate only
 	return rt::mk(fmaf(cs, v.x, sn * v.z), v.y, fmaf(-sn, v.x, cs * v.z));
 }
 

@@ -623,8 +623,9 @@ struct Flattener {
 		prim_boxes.push_back(b);
 	}
 	static bool is_identity(const Xf& x) { return !x.rot && !x.tr; }
-	static void put_xf(float* q, const Xf& x) {   // (cos, sin, off.x, off.y), (off.z, 0, 0, 0)
+	static void put_xf(float* q, const Xf& x) {   // (cos, sin, off.x, off.y), (off.z, rotates ? 1 : 0, 0, 0)
 		q[0] = x.rot ? x.c : 1.0f; q[1] = x.rot ? x.s : 0.0f; q[2] = x.off[0]; q[3] = x.off[1]; q[4] = x.off[2];
+		q[5] = x.rot ? 1.0f : 0.0f;   // a translate-only instance must not run vectors through an identity rotation: fma(1, -0, 0 * z) is +0
 	}
 	// World bounds of an instanced primitive are computed with host rounding, the hit with the
 	// kernel's ray transform: pad so the box always contains what the kernel can hit.

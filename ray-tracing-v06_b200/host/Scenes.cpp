@@ -22,6 +22,7 @@
 
 #include "rt_engine/geometry/BVH.cuh"
 #include "rt_engine/geometry/HittableList.cuh"
+#include "rt_engine/geometry/Mesh.cuh"
 #include "rt_engine/geometry/Quad.cuh"
 #include "rt_engine/geometry/SphereHittable.cuh"
 #include "rt_engine/shaders/cu_Cameras.cuh"
@@ -386,6 +387,57 @@ void build_book2_final(rtb_scene_info* info) {
 	finish(info, k.list(world), book2_camera(glm::vec3(478, 278, -600), glm::vec3(278, 278, 0), 40.0f, 1.0f), 800, 800, 10000, 40, true);
 }
 
+// A procedural triangle mesh (a subdivided icosahedron, 1,280 faces) written to and read back through the OBJ
+// loader: the triangle path of the renderer on a closed mesh, glass over a checkered ground, next to a metal copy.
+std::string write_icosphere_obj(int subdivisions) {
+	std::vector<glm::vec3> v; std::vector<int> f;
+	const float t = (1.0f + sqrtf(5.0f)) * 0.5f;
+	const float P[12][3] = {{-1, t, 0}, {1, t, 0}, {-1, -t, 0}, {1, -t, 0}, {0, -1, t}, {0, 1, t}, {0, -1, -t}, {0, 1, -t}, {t, 0, -1}, {t, 0, 1}, {-t, 0, -1}, {-t, 0, 1}};
+	const int F[20][3] = {{0, 11, 5}, {0, 5, 1}, {0, 1, 7}, {0, 7, 10}, {0, 10, 11}, {1, 5, 9}, {5, 11, 4}, {11, 10, 2}, {10, 7, 6}, {7, 1, 8},
+	                      {3, 9, 4}, {3, 4, 2}, {3, 2, 6}, {3, 6, 8}, {3, 8, 9}, {4, 9, 5}, {2, 4, 11}, {6, 2, 10}, {8, 6, 7}, {9, 8, 1}};
+	for (auto& p : P) v.push_back(glm::normalize(glm::vec3(p[0], p[1], p[2])));
+	for (auto& q : F) { f.push_back(q[0]); f.push_back(q[1]); f.push_back(q[2]); }
+	for (int s = 0; s < subdivisions; ++s) {
+		std::vector<int> nf; std::map<std::pair<int, int>, int> mid;
+		auto midpoint = [&](int a, int b) {
+			auto key = std::make_pair(a < b ? a : b, a < b ? b : a);
+			auto it = mid.find(key); if (it != mid.end()) return it->second;
+			v.push_back(glm::normalize((v[a] + v[b]) * 0.5f)); return mid[key] = (int)v.size() - 1;
+		};
+		for (size_t k = 0; k < f.size(); k += 3) {
+			int a = f[k], b = f[k + 1], c = f[k + 2], ab = midpoint(a, b), bc = midpoint(b, c), ca = midpoint(c, a);
+			int tri[12] = {a, ab, ca, b, bc, ab, c, ca, bc, ab, bc, ca};
+			nf.insert(nf.end(), tri, tri + 12);
+		}
+		f.swap(nf);
+	}
+	std::string path = "/tmp/rtb_icosphere_" + std::to_string(subdivisions) + ".obj";
+	FILE* o = fopen(path.c_str(), "w");
+	if (!o) throw std::runtime_error("cannot write " + path);
+	fprintf(o, "# icosphere, %zu vertices, %zu faces\n", v.size(), f.size() / 3);
+	for (auto& p : v) fprintf(o, "v %.9g %.9g %.9g\n", p.x, p.y, p.z);
+	for (size_t k = 0; k < f.size(); k += 3) fprintf(o, "f %d//%d %d//%d %d//%d\n", f[k] + 1, f[k] + 1, f[k + 1] + 1, f[k + 1] + 1, f[k + 2] + 1, f[k + 2] + 1);
+	fclose(o);
+	return path;
+}
+
+void build_mesh_icospheres(rtb_scene_info* info) {
+	Keep k;
+	Mesh mesh = MeshHandle::LoadObj(write_icosphere_obj(3));
+	auto even = k.tex(new solid_texture(glm::vec3(.2f, .3f, .1f)));
+	auto odd = k.tex(new solid_texture(glm::vec3(.9f, .9f, .9f)));
+	auto ground = k.mat(new Lambertian(k.tex(new checker_texture(even, odd, 0.8f))));
+	auto glass = k.mat(new Dielectric(glm::vec3(1.0f), 1.5f));
+	auto metal = k.mat(new Metal(glm::vec3(0.8f, 0.6f, 0.2f), 0.05f));
+	std::vector<MeshHandle> meshes;
+	meshes.push_back(MeshHandle::MakeMesh(mesh, glass));
+	meshes.push_back(MeshHandle::MakeMesh(mesh, metal));
+	std::vector<const Hittable*> objs{k.quad(glm::vec3(-20, -1, -20), glm::vec3(40, 0, 0), glm::vec3(0, 0, 40), ground),
+	                                  k.translate(meshes[0].getHittablePtr(), glm::vec3(-1.2f, 0, 0)),
+	                                  k.translate(k.rotate_y(meshes[1].getHittablePtr(), 30.0f), glm::vec3(1.2f, 0, 0.5f))};
+	finish(info, k.list(objs), book2_camera(glm::vec3(0, 1.5f, -6), glm::vec3(0, 0, 0), 35.0f, 400.0f / 225.0f), 400, 225, 100, 50, false);
+}
+
 struct Entry { const char* name; void (*build)(rtb_scene_info*); };
 const Entry kScenes[] = {
     {"book1_final", build_book1_final},           {"book2_bouncing", build_book2_bouncing},
@@ -393,6 +445,7 @@ const Entry kScenes[] = {
     {"book2_perlin", build_book2_perlin},         {"book2_quads", build_book2_quads},
     {"book2_simple_light", build_book2_simple_light}, {"book2_cornell", build_book2_cornell},
     {"book2_cornell_smoke", build_book2_cornell_smoke}, {"book2_final", build_book2_final},
+    {"mesh_icospheres", build_mesh_icospheres},
 };
 
 }  // namespace

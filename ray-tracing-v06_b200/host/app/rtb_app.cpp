@@ -3,6 +3,7 @@
 // build the camera, build the scene, MakeRenderer, Render, DownloadRenderbuffer, write the image.
 //
 //   rtb_app [scene] [--width W] [--height H] [--spp N] [--depth D] [--out image.ppm|image.pfm]
+//   rtb_app --obj model.obj [...]     a Wavefront OBJ mesh (MeshHandle) on a checkered floor under the sky
 //
 // scene = one of rtb_scenes_name(i) (default book2_bouncing, which goes through SceneBook2BVH::Factory
 // and Renderer::MakeRenderer exactly like FirstApp::MakeApp).  The 8-bit writer follows
@@ -17,9 +18,13 @@
 
 #include "Renderer.h"
 #include "rt_engine/geometry/BVH.cuh"
+#include "rt_engine/geometry/HittableList.cuh"
+#include "rt_engine/geometry/Mesh.cuh"
 #include "rt_engine/geometry/Scenes.h"
 #include "rt_engine/geometry/SphereHittable.cuh"
 #include "rt_engine/shaders/cu_Cameras.cuh"
+#include "rt_engine/shaders/cu_Textures.cuh"
+#include "rt_engine/shaders/cu_materials.cuh"
 
 static bool write_image(const std::string& path, uint32_t width, uint32_t height, const std::vector<glm::vec4>& data) {
 	FILE* f = fopen(path.c_str(), "wb");
@@ -44,7 +49,7 @@ static bool write_image(const std::string& path, uint32_t width, uint32_t height
 }
 
 int main(int argc, char** argv) {
-	std::string scene_name = "book2_bouncing", out = "render.ppm";
+	std::string scene_name = "book2_bouncing", out = "render.ppm", obj_path;
 	int width = 0, height = 0, spp = 0, depth = 0;
 	for (int i = 1; i < argc; ++i) {
 		std::string a = argv[i];
@@ -54,12 +59,36 @@ int main(int argc, char** argv) {
 		else if (a == "--spp") spp = next();
 		else if (a == "--depth") depth = next();
 		else if (a == "--out" && i + 1 < argc) out = argv[++i];
+		else if (a == "--obj" && i + 1 < argc) obj_path = argv[++i];
 		else if (a == "--list") { for (int k = 0; k < rtb_scenes_count(); ++k) printf("%s\n", rtb_scenes_name(k)); return 0; }
 		else scene_name = a;
 	}
 	try {
 		std::vector<glm::vec4> fb;
-		if (scene_name == "book2_bouncing") {
+		if (!obj_path.empty()) {
+			// A mesh scene assembled the way FirstApp assembles its world: materials, handles, a HittableList, MakeRenderer.
+			uint32_t _width = width ? width : 800, _height = height ? height : 600;
+			printf("Loading %s... ", obj_path.c_str());
+			Mesh mesh = MeshHandle::LoadObj(obj_path);
+			Lambertian clay(glm::vec3(0.73f, 0.73f, 0.73f));
+			MeshHandle model = MeshHandle::MakeMesh(mesh, &clay);
+			printf("%d triangles.\n", model.triangleCount());
+			const glm::vec3 lo = model.getBounds().getMin(), hi = model.getBounds().getMax(), mid = (lo + hi) * 0.5f;
+			const float size = glm::length(hi - lo);
+			solid_texture dark(glm::vec3(.2f, .3f, .1f)), light(glm::vec3(.9f, .9f, .9f));
+			checker_texture checks(&dark, &light, 8.0f / size);
+			Lambertian floor_mat(&checks);
+			GeoHandle floor = GeoHandle::MakeQuad(Quad(glm::vec3(mid.x - 10 * size, lo.y, mid.z - 10 * size), glm::vec3(20 * size, 0, 0), glm::vec3(0, 0, 20 * size)), &floor_mat);
+			const Hittable* objs[2] = {floor.getHittablePtr(), model.getHittablePtr()};
+			aabb bounds = model.getBounds(); bounds += floor.getBounds();
+			HittableList world(objs, 2, bounds);
+			MotionBlurCamera cam(mid + glm::vec3(0.55f, 0.35f, 1.1f) * size, mid, glm::vec3(0, 1, 0), 40.0f, _width / (float)_height, 0.0f, 1.0f);
+			Renderer renderer = Renderer::MakeRenderer(_width, _height, spp ? spp : 64, depth ? depth : 16, &cam, &world);
+			renderer.Render();
+			fb.resize((size_t)_width * _height);
+			renderer.DownloadRenderbuffer(fb.data());
+			width = _width; height = _height;
+		} else if (scene_name == "book2_bouncing") {
 			// FirstApp::MakeApp, statement for statement, with the resolution / spp / depth made arguments
 			uint32_t _width = width ? width : 1280, _height = height ? height : 720;
 			printf("Building MotionBlurCamera object... ");

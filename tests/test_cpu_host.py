@@ -101,6 +101,8 @@ def test_flattener(rtb):
     assert all(v["depth"] <= 30 for v in stats.values())
     s = rtb.Scene(); s.set_root(s.sphere((0, 0, 0), 1.0, s.lambertian(albedo=(1, 1, 1))))
     assert s.flatten_stats() == {"primitives": 1, "record_slots": 1, "inner_nodes": 0, "depth": 1}
+    # the OBJ mesh scene: two instanced copies of a 1,280-face icosphere read back through MeshHandle::LoadObj, plus the ground quad
+    assert stats["mesh_icospheres"]["primitives"] == 2 * 1280 + 1 and stats["mesh_icospheres"]["record_slots"] == 2 * 2 * 1280 + 1
 
 
 def test_host_mirror_scene_registry(rtb):
@@ -157,3 +159,45 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert k in line, k
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["vs_baseline"] is None
+
+
+def test_obj_mesh_loader(rtb, tmp_path):
+    """MeshHandle::LoadObj / MakeMesh (host/rt_engine/geometry/Mesh.cuh): `v` and `f` records, `i/j/k` corners,
+    negative indices, polygons fanned into triangles, degenerate faces dropped; one Triangle per face under a BVH."""
+    import subprocess
+    (tmp_path / "m.obj").write_text(
+        "# a unit cube side, a fan, and junk the loader must skip\n"
+        "o thing\nvn 0 0 1\nvt 0.5 0.5\n"
+        "v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\n"
+        "f 1/1/1 2/1/1 3/1/1 4/1/1\n"          # quad -> 2 triangles
+        "v 0 0 1\n"
+        "f -1 -5 -4\n"                          # relative indices: (0,0,1), (0,0,0), (1,0,0)
+        "f 1//1 1//1 2//1\n"                    # degenerate: dropped
+        "s off\n")
+    (tmp_path / "m.cpp").write_text(r'''
+#include <cstdio>
+#include <vector>
+#include "rt_engine/geometry/Mesh.cuh"
+#include "rt_engine/shaders/cu_materials.cuh"
+int main(int, char** argv) {
+	Mesh m = MeshHandle::LoadObj(argv[1]);
+	Lambertian grey(glm::vec3(0.5f));
+	MeshHandle h = MeshHandle::MakeMesh(m, &grey);
+	rtb_scene_set_root(rtb_host::scene(), h.getHittablePtr()->rtb_object);
+	size_t n = rtb_scene_serialize(rtb_host::scene(), nullptr, 0);
+	std::vector<unsigned char> blob(n); rtb_scene_serialize(rtb_host::scene(), blob.data(), n);
+	FILE* f = fopen(argv[2], "wb"); fwrite(blob.data(), 1, n, f); fclose(f);
+	printf("%zu %zu %d\n", m.vertices.size(), m.indices.size() / 3, h.triangleCount());
+	try { MeshHandle::LoadObj("/nonexistent.obj"); return 1; } catch (const std::exception&) {}
+	return 0;
+}''')
+    pkg = ROOT / "ray-tracing-v06_b200"
+    subprocess.run(["g++", "-std=c++20", "-O1", f"-I{pkg / 'host'}", f"-I{pkg / 'host' / 'glm_compat'}", f"-I{ROOT / 'include'}", "-I/usr/local/cuda/include",
+                    "-o", str(tmp_path / "m"), str(tmp_path / "m.cpp"), f"-L{pkg}", "-lrtb200", f"-Wl,-rpath,{pkg}"], check=True, capture_output=True)
+    out = subprocess.run([str(tmp_path / "m"), str(tmp_path / "m.obj"), str(tmp_path / "m.rtbs")], check=True, capture_output=True, text=True).stdout.split()
+    assert out == ["5", "4", "3"]                       # 5 vertices, 4 faces after fanning, 3 with area
+    h, mats, objs, children = parse_blob((tmp_path / "m.rtbs").read_bytes())
+    tris = [o for o in objs if o["kind"] == 3]
+    assert len(tris) == 3 and objs[int(h["root_object"])]["kind"] == 6 and len(children) == 3
+    got = sorted(tuple(np.round(t["f"][:9], 6)) for t in tris)          # Q, u, v
+    assert got == sorted([(0, 0, 0, 1, 0, 0, 1, 1, 0), (0, 0, 0, 1, 1, 0, 0, 1, 0), (0, 0, 1, 0, 0, -1, 1, 0, -1)])

@@ -76,7 +76,7 @@ def test_hit_records_bit_exact(rtb, orc, renderer, name, lo, hi):
     assert n > 10_000
 
 
-@pytest.mark.parametrize("name,lo,hi", [("book2_cornell", 0, 555), ("book2_final", -200, 600)])
+@pytest.mark.parametrize("name,lo,hi", [("book2_cornell", 0, 555), ("book2_final", -200, 600), ("mesh_icospheres", -4, 4)])
 def test_hit_records_instanced_bit_exact(rtb, orc, renderer, name, lo, hi):
     """translate(rotate_y(x)) instances: the kernels take the ray into the primitive's frame with the
     same operations as the book's translate::hit / rotate_y::hit, so hits stay bit-exact."""
@@ -146,6 +146,7 @@ IMAGE_CASES = [
     ("book2_cornell", 100, 100, 8, 50, 0.01),
     ("book2_cornell_smoke", 100, 100, 8, 50, 0.02),
     ("book2_final", 100, 100, 8, 40, 0.02),
+    ("mesh_icospheres", 160, 90, 4, 50, 0.01),     # 2 x 1,280 OBJ triangles, instanced, glass and metal
 ]
 
 
@@ -230,6 +231,29 @@ def test_cli_app_matches_the_library(rtb, renderer, tmp_path):
     renderer.render(W, H, 0, SPP, D, seed=1984)
     ref = (renderer.download()[::-1, :, :3] * np.float32(255.999)).astype(np.uint8)
     assert np.array_equal(img, ref)
+
+
+def test_cli_app_renders_an_obj_mesh(tmp_path):
+    """rtb_app --obj: MeshHandle::LoadObj -> MakeMesh -> HittableList -> Renderer::MakeRenderer.  An octahedron of grey
+    clay on the checkered floor under the sky: the centre of the image is the mesh (grey, r == g == b up to noise),
+    the top row is sky (blue-ish), the bottom rows are floor."""
+    import subprocess
+    from conftest import ROOT
+    (tmp_path / "octa.obj").write_text("v 1 0 0\nv -1 0 0\nv 0 1 0\nv 0 -1 0\nv 0 0 1\nv 0 0 -1\n"
+                                       "f 1 3 5\nf 3 2 5\nf 2 4 5\nf 4 1 5\nf 3 1 6\nf 2 3 6\nf 4 2 6\nf 1 4 6\n")
+    out = tmp_path / "octa.ppm"
+    W, H = 120, 90
+    log = subprocess.run([str(ROOT / "ray-tracing-v06_b200" / "rtb_app"), "--obj", str(tmp_path / "octa.obj"), "--width", str(W), "--height", str(H),
+                          "--spp", "64", "--depth", "8", "--out", str(out)], check=True, capture_output=True, text=True).stdout
+    assert "8 triangles" in log
+    raw = out.read_bytes(); header = f"P6\n{W} {H}\n255\n".encode()
+    assert raw.startswith(header)
+    img = np.frombuffer(raw[len(header):], dtype=np.uint8).reshape(H, W, 3).astype(np.int32)
+    centre = img[H // 2 - 3:H // 2 + 3, W // 2 - 3:W // 2 + 3].reshape(-1, 3).mean(axis=0)
+    sky = img[0].mean(axis=0)
+    assert sky[2] > sky[0] + 20                                     # sky gradient: blue over red at the top
+    assert abs(centre[0] - centre[2]) < 25 and 40 < centre.mean() < 250   # grey clay lit by the sky
+    assert img.std() > 10
 
 
 def test_edge_cases_gpu(rtb, orc, renderer):
