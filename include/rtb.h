@@ -108,8 +108,13 @@ int rtb_scene_set_background(rtb_scene* s, int mode, const float rgb[3]);
 /* Which tree the renderer walks.  Closest hits do not depend on it (tests/test_gpu_parity.py checks that).
  * RTB_WORLD_BVH_QUALITY (default): a binned-SAH tree over all flattened primitives.
  * RTB_WORLD_BVH_AS_BUILT: when the scene root is a BVH, exactly the tree its BVH_Handle::Factory builder makes
- * (same nodes, same primitive order as the reference), e.g. to inspect it with rtb_scene_world_bvh. */
-enum rtb_world_bvh_mode { RTB_WORLD_BVH_QUALITY = 0, RTB_WORLD_BVH_AS_BUILT = 1 };
+ * (same nodes, same primitive order as the reference), e.g. to inspect it with rtb_scene_world_bvh.
+ * RTB_WORLD_BVH_GPU_LBVH: a linear BVH (Morton codes, radix sort, one-pass hierarchy, bottom-up fit) built on the
+ * renderer's device inside rtb_renderer_set_scene: a lower-quality tree in a fraction of the build time, for large
+ * meshes and scenes that are rebuilt often.  Needs a renderer: rtb_scene_flatten_stats refuses it.  Trees up to 62
+ * levels deep are walked (on a 64-entry stack past 30 levels); a deeper one is replaced by the RTB_WORLD_BVH_QUALITY
+ * tree (rtb_scene_stats.builder says which builder produced the tree in use). */
+enum rtb_world_bvh_mode { RTB_WORLD_BVH_QUALITY = 0, RTB_WORLD_BVH_AS_BUILT = 1, RTB_WORLD_BVH_GPU_LBVH = 2 };
 int rtb_scene_set_world_bvh(rtb_scene* s, int mode);
 
 int rtb_scene_num_objects(const rtb_scene* s);
@@ -143,6 +148,18 @@ int rtb_scene_world_bvh(const rtb_scene* s, rtb_bvh_node* nodes_out, int cap, in
  * reports its sizes; also fills the world BVH returned by rtb_scene_world_bvh.  out4 = {primitives
  * (BVH leaves), 64-byte record slots, inner nodes of the wide layout, tree depth}. */
 int rtb_scene_flatten_stats(rtb_scene* s, int32_t out4[4]);
+
+/* What rtb_renderer_set_scene last built (declared below with the renderer): sizes as in rtb_scene_flatten_stats,
+ * the builder that produced the tree the kernels walk (an rtb_world_bvh_mode value, or RTB_BUILDER_MEDIAN_FALLBACK
+ * when both the requested tree and the SAH tree were deeper than the traversal stack), and host wall-clock times. */
+enum { RTB_BUILDER_MEDIAN_FALLBACK = 3 };
+typedef struct rtb_scene_stats {
+	int32_t primitives, record_slots, inner_nodes, depth;
+	int32_t builder;
+	float flatten_ms;     /* whole flatten: graph walk, BVH build, wide-layout conversion */
+	float bvh_build_ms;   /* the BVH build alone (GPU LBVH: upload of boxes, kernels, download of nodes) */
+	int32_t reserved;
+} rtb_scene_stats;
 
 /* ------------------------------------------------------------------ cameras */
 
@@ -198,6 +215,8 @@ int  rtb_renderer_set_scene(rtb_renderer* r, rtb_scene* s);
 int  rtb_renderer_set_camera(rtb_renderer* r, const rtb_camera* cam);
 /* Bytes of the scene arena rtb_renderer_set_scene copies host -> device. */
 size_t rtb_renderer_scene_bytes(const rtb_renderer* r);
+/* Sizes, builder and build times of the scene last flattened by rtb_renderer_set_scene. */
+int  rtb_renderer_scene_stats(const rtb_renderer* r, rtb_scene_stats* out);
 /* Renders asynchronously on `stream`, ADDING radiance sums into the accumulators. */
 int  rtb_render(rtb_renderer* r, const rtb_render_params* p, void* stream);
 int  rtb_synchronize(rtb_renderer* r);

@@ -26,7 +26,8 @@ RTB_OK = 0
 TEX_SOLID, TEX_CHECKER, TEX_IMAGE, TEX_NOISE = 0, 1, 2, 3
 BVH_TOPDOWN_MEDIAN, BVH_TOPDOWN_SAH, BVH_BOTTOMUP = 0, 1, 2
 BG_SKY_GRADIENT, BG_CONSTANT = 0, 1
-WORLD_BVH_QUALITY, WORLD_BVH_AS_BUILT = 0, 1
+WORLD_BVH_QUALITY, WORLD_BVH_AS_BUILT, WORLD_BVH_GPU_LBVH = 0, 1, 2
+BUILDER_NAMES = {0: "host_sah", 1: "as_built", 2: "gpu_lbvh", 3: "host_median_fallback"}
 CAM_PINHOLE, CAM_DEFOCUS, CAM_MOTION = 0, 1, 2
 RENDER_CLEAR, RENDER_VARIANCE = 1, 2
 MISS_DIST = np.float32(3.402823466e38)
@@ -60,6 +61,11 @@ class RenderParams(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("launches", C.c_uint64), ("batches", C.c_uint64), ("render_ms", C.c_double)]
+
+
+class SceneStats(C.Structure):
+    _fields_ = [("primitives", C.c_int32), ("record_slots", C.c_int32), ("inner_nodes", C.c_int32), ("depth", C.c_int32), ("builder", C.c_int32),
+                ("flatten_ms", C.c_float), ("bvh_build_ms", C.c_float), ("reserved", C.c_int32)]
 
 
 class Profile(C.Structure):
@@ -124,6 +130,7 @@ ABI = {
     "rtb_renderer_set_scene": (C.c_int, [_P, _P]),
     "rtb_renderer_set_camera": (C.c_int, [_P, C.POINTER(Camera)]),
     "rtb_renderer_scene_bytes": (C.c_size_t, [_P]),
+    "rtb_renderer_scene_stats": (C.c_int, [_P, C.POINTER(SceneStats)]),
     "rtb_render": (C.c_int, [_P, C.POINTER(RenderParams), _P]),
     "rtb_synchronize": (C.c_int, [_P]),
     "rtb_renderer_accum_ptr": (_P, [_P]),
@@ -337,6 +344,13 @@ class Renderer:
 
     def scene_bytes(self) -> int:
         return int(lib().rtb_renderer_scene_bytes(self.handle))
+
+    def scene_stats(self) -> dict:
+        """Sizes, builder and host build times of the scene last flattened by set_scene (rtb_scene_stats)."""
+        st = SceneStats()
+        _check(lib().rtb_renderer_scene_stats(self.handle, C.byref(st)), "rtb_renderer_scene_stats")
+        return {"primitives": st.primitives, "record_slots": st.record_slots, "inner_nodes": st.inner_nodes, "depth": st.depth,
+                "builder": BUILDER_NAMES.get(st.builder, str(st.builder)), "flatten_ms": st.flatten_ms, "bvh_build_ms": st.bvh_build_ms}
 
     def set_camera(self, cam: Camera):
         _check(lib().rtb_renderer_set_camera(self.handle, C.byref(cam)), "rtb_renderer_set_camera")

@@ -27,6 +27,7 @@ using rt::v3;
 #endif
 #define SHADE_THREADS 256
 #define STREAM_THREADS 256
+#define DEEP_STACK_SIZE 64
 #ifndef STACK_SIZE
 #define STACK_SIZE 32
 #endif
@@ -721,10 +722,10 @@ texture_kernel(SceneView sv, WaveView wv, uint32_t bounce) {
 // One persistent launch then runs every remaining path to completion (traverse + shade fused, one
 // thread per path); later traverse/shade launches of the batch see tail_from and return at once.
 
-template <bool MEDIA>
+template <bool MEDIA, int STACK>
 __global__ void __launch_bounds__(TRAVERSE_THREADS)
 tail_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce0, uint32_t threshold) {
-	__shared__ int s_stack[STACK_SIZE * TRAVERSE_THREADS];
+	__shared__ int s_stack[STACK * TRAVERSE_THREADS];
 	if (*wv.tail_from < bounce0) return;                 // an earlier checkpoint already took the batch over
 	const uint32_t n = wv.n_live[bounce0];
 	if (n == 0 || n > threshold) return;
@@ -809,10 +810,11 @@ resolve_kernel(const float4* __restrict__ accum, float4* __restrict__ out, uint3
 // ------------------------------------------------------------------------------------------------
 // hit-record parity hook
 
+template <int STACK>
 __global__ void __launch_bounds__(TRAVERSE_THREADS)
 trace_rays_kernel(SceneView sv, const float4* __restrict__ ro, const float4* __restrict__ rd, uint32_t n,
                   int2* __restrict__ hit, int2* __restrict__ stats, uint32_t* counter) {
-	__shared__ int s_stack[STACK_SIZE * TRAVERSE_THREADS];
+	__shared__ int s_stack[STACK * TRAVERSE_THREADS];
 	const int lane = threadIdx.x & 31;
 	for (;;) {
 		uint32_t base = 0;
@@ -874,8 +876,8 @@ void query_occupancy(int device, LaunchCfg& lc) {
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, generate_kernel, STREAM_THREADS, 0);
 	int occ_trav = occ_t < occ_tm ? occ_t : occ_tm;
 	int occ_l = 0, occ_lm = 0;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, tail_kernel<false>, TRAVERSE_THREADS, 0);
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lm, tail_kernel<true>, TRAVERSE_THREADS, 0);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, tail_kernel<false, STACK_SIZE>, TRAVERSE_THREADS, 0);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lm, tail_kernel<true, STACK_SIZE>, TRAVERSE_THREADS, 0);
 	int occ_tail = occ_l < occ_lm ? occ_l : occ_lm;
 	lc.blocks_tail = sms * (occ_tail > 0 ? occ_tail : 1);
 	lc.sms = sms;
@@ -889,9 +891,12 @@ void launch_generate(const BatchParams& bp, const rtb_camera& cam, const WaveVie
 }
 void launch_traverse(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st) {
 	// media need the per-path RNG inside traversal; scenes without media skip that code entirely
-	const bool small = sv.tree_depth <= 17;   // a walk keeps at most depth - 1 entries on its stack
+	// a walk keeps at most depth - 1 entries on its stack: 16 entries for shallow trees, 32 normally, 64 for the deep
+	// trees a linear BVH over a large mesh can be (the flattener never hands over more than RTB_TREE_DEPTH_MAX levels)
+	const bool small = sv.tree_depth <= 17, deep = sv.tree_depth > STACK_SIZE - 2;
 #define RTB_LAUNCH_TRAVERSE(M) \
 	do { if (small) traverse_kernel<M, 16><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce); \
+	     else if (deep) traverse_kernel<M, DEEP_STACK_SIZE><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce); \
 	     else traverse_kernel<M, STACK_SIZE><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce); } while (0)
 	if (sv.has_media == 0) RTB_LAUNCH_TRAVERSE(0);
 	else if (sv.has_media == 1) RTB_LAUNCH_TRAVERSE(1);
@@ -899,8 +904,14 @@ void launch_traverse(const SceneView& sv, const BatchParams& bp, const WaveView&
 #undef RTB_LAUNCH_TRAVERSE
 }
 void launch_tail(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, uint32_t threshold, const LaunchCfg& lc, cudaStream_t st) {
-	if (sv.has_media) tail_kernel<true><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, threshold);
-	else tail_kernel<false><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, threshold);
+	const bool deep = sv.tree_depth > STACK_SIZE - 2;
+	if (sv.has_media) {
+		if (deep) tail_kernel<true, DEEP_STACK_SIZE><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, threshold);
+		else tail_kernel<true, STACK_SIZE><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, threshold);
+	} else {
+		if (deep) tail_kernel<false, DEEP_STACK_SIZE><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, threshold);
+		else tail_kernel<false, STACK_SIZE><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, threshold);
+	}
 }
 void launch_shade(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st) {
 	shade_kernel<<<lc.blocks_shade, SHADE_THREADS, 0, st>>>(sv, bp, wv, bounce);
@@ -920,7 +931,8 @@ void launch_resolve(const float4* accum, float4* out, uint32_t n, cudaStream_t s
 void launch_trace_rays(const SceneView& sv, const float4* ray_o, const float4* ray_d, uint32_t n, int2* hit_tmp, int2* stats_tmp,
                        rtb_hit* hits_out, uint32_t* work_counter, const LaunchCfg& lc, cudaStream_t st) {
 	cudaMemsetAsync(work_counter, 0, sizeof(uint32_t), st);
-	trace_rays_kernel<<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, ray_o, ray_d, n, hit_tmp, stats_tmp, work_counter);
+	if (sv.tree_depth > STACK_SIZE - 2) trace_rays_kernel<DEEP_STACK_SIZE><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, ray_o, ray_d, n, hit_tmp, stats_tmp, work_counter);
+	else trace_rays_kernel<STACK_SIZE><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, ray_o, ray_d, n, hit_tmp, stats_tmp, work_counter);
 	hit_record_kernel<<<lc.blocks_stream, STREAM_THREADS, 0, st>>>(sv, ray_o, ray_d, hit_tmp, stats_tmp, n, hits_out);
 }
 

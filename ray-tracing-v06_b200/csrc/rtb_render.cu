@@ -38,6 +38,8 @@ struct rtb_renderer {
 	SceneView staged_sv{};
 	uint64_t staged_uid = 0, staged_version = 0;
 	bool has_scene = false;
+	rtb_scene_stats scene_stats{};
+	GpuScratch build_scratch;   // grow-only scratch of the GPU BVH build
 	uint64_t scene_version = 0;
 	rtb_camera cam{};
 	bool has_cam = false;
@@ -126,11 +128,19 @@ void rtb_renderer_destroy(rtb_renderer* r) {
 	cudaSetDevice(r->device);
 	cudaStreamSynchronize(r->stream);
 	free_graph(r);
+	free_gpu_scratch(r->build_scratch);
 	for (cudaEvent_t e : r->prof_events) cudaEventDestroy(e);
 	cudaFree(r->d_scene); cudaFree(r->d_accum); cudaFree(r->d_accum2); cudaFree(r->d_out); cudaFree(r->d_wave);
 	cudaEventDestroy(r->ev_in); cudaEventDestroy(r->ev_out); cudaEventDestroy(r->ev_t0); cudaEventDestroy(r->ev_t1);
 	cudaStreamDestroy(r->stream);
 	delete r;
+}
+
+int rtb_renderer_scene_stats(const rtb_renderer* r, rtb_scene_stats* out) {
+	if (!r || !out) return fail(RTB_ERR_INVALID, "rtb_renderer_scene_stats: null argument");
+	if (!r->has_scene) return fail(RTB_ERR_STATE, "rtb_renderer_scene_stats: no scene set");
+	*out = r->scene_stats;
+	return RTB_OK;
 }
 
 int rtb_renderer_set_scene(rtb_renderer* r, rtb_scene* s) {
@@ -140,8 +150,10 @@ int rtb_renderer_set_scene(rtb_renderer* r, rtb_scene* s) {
 	const bool cached = r->staged_uid == s->uid && r->staged_version == s->version && !r->staging.empty();
 	if (!cached) {
 		FlatScene fs;
-		int rc = flatten(*s, fs);
+		GpuBuildContext gpu{r->device, r->stream, &r->build_scratch};
+		int rc = flatten(*s, fs, &gpu);
 		if (rc) return rc;
+		r->scene_stats = rtb_scene_stats{fs.n_items, (int32_t)fs.prims.size(), (int32_t)fs.nodes.size(), fs.max_depth_nodes, fs.builder, fs.flatten_ms, fs.bvh_build_ms, 0};
 		// one arena, every section 256-byte aligned
 		size_t off_nodes = 0;
 		size_t off_prims = align_up(off_nodes + fs.nodes.size() * sizeof(DevNode), 256);

@@ -12,9 +12,12 @@
 #include <algorithm>
 #include <atomic>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <functional>
+#include <future>
+#include <thread>
 
 #include "rtmath.h"
 
@@ -261,7 +264,7 @@ int rtb_scene_set_root(rtb_scene* s, int object) {
 	s->root = object; s->version++; return RTB_OK;
 }
 int rtb_scene_set_world_bvh(rtb_scene* s, int mode) {
-	if (!s || (mode != RTB_WORLD_BVH_QUALITY && mode != RTB_WORLD_BVH_AS_BUILT)) return fail(RTB_ERR_INVALID, "rtb_scene_set_world_bvh: bad mode");
+	if (!s || (mode != RTB_WORLD_BVH_QUALITY && mode != RTB_WORLD_BVH_AS_BUILT && mode != RTB_WORLD_BVH_GPU_LBVH)) return fail(RTB_ERR_INVALID, "rtb_scene_set_world_bvh: bad mode");
 	s->world_bvh_mode = mode; s->version++; return RTB_OK;
 }
 int rtb_scene_set_background(rtb_scene* s, int mode, const float rgb[3]) {
@@ -502,16 +505,22 @@ int build_bvh_world_sah(const std::vector<Box3>& boxes, std::vector<rtb_bvh_node
 	std::vector<int> idx(n); for (int i = 0; i < n; ++i) idx[i] = i;
 	std::vector<float> cen(3 * (size_t)n);
 	for (int i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) cen[3 * (size_t)i + a] = 0.5f * (boxes[i].mn[a] + boxes[i].mx[a]);
-	nodes.clear(); nodes.reserve(2 * (size_t)n);
-	auto push = [&](const Box3& b, int l, int r) {
-		rtb_bvh_node nd; memcpy(nd.bmin, b.mn, 12); memcpy(nd.bmax, b.mx, 12); nd.left_child_idx = l; nd.right_child_hittable_idx = r;
-		nodes.push_back(nd); return (int)nodes.size() - 1;
+	// Nodes are stored in post-order (children before their parent, root last, like the reference's builders).  A
+	// subtree over k leaves then owns 2k - 1 consecutive slots starting at a base known before it is built (left child:
+	// the parent's base; right child: past the left subtree), whatever the splits inside it are, so large subtrees are
+	// built by concurrent tasks writing disjoint slot and index ranges: the same array as a serial build.
+	nodes.assign(2 * (size_t)n - 1, rtb_bvh_node{});
+	auto put = [&](int slot, const Box3& b, int l, int r) {
+		rtb_bvh_node& nd = nodes[slot]; memcpy(nd.bmin, b.mn, 12); memcpy(nd.bmax, b.mx, 12); nd.left_child_idx = l; nd.right_child_hittable_idx = r;
+		return slot;
 	};
-	const int NB = 32, MAX_DEPTH = 26;
-	std::function<int(int, int, int)> rec = [&](int start, int end, int depth) -> int {
+	const int NB = 32, MAX_DEPTH = 26, PARALLEL_MIN = 16384;
+	const int max_fork_depth = n >= 2 * PARALLEL_MIN ? std::min(6, (int)std::ceil(std::log2(std::max(2u, std::thread::hardware_concurrency())))) + 1 : 0;
+	std::function<int(int, int, int, int)> rec = [&](int start, int end, int depth, int base) -> int {
+		const int slot = base + 2 * (end - start) - 2;      // this subtree's root: last of its 2 (end - start) - 1 slots
 		Box3 bounds = empty_box();
 		for (int i = start; i < end; ++i) grow(bounds, boxes[idx[i]]);
-		if (end - start == 1) return push(bounds, -1, start);
+		if (end - start == 1) return put(slot, bounds, -1, start);
 		float cmn[3] = {INFINITY, INFINITY, INFINITY}, cmx[3] = {-INFINITY, -INFINITY, -INFINITY};
 		for (int i = start; i < end; ++i) for (int a = 0; a < 3; ++a) {
 			float c = cen[3 * (size_t)idx[i] + a]; cmn[a] = std::fmin(cmn[a], c); cmx[a] = std::fmax(cmx[a], c);
@@ -558,11 +567,18 @@ int build_bvh_world_sah(const std::vector<Box3>& boxes, std::vector<rtb_bvh_node
 				return cx < cy || (cx == cy && x < y);
 			});
 		}
-		int l = rec(start, mid, depth + 1);
-		int r = rec(mid, end, depth + 1);
-		return push(bounds, l, r);
+		int l, r;
+		if (depth < max_fork_depth && end - start >= 2 * PARALLEL_MIN && mid - start >= PARALLEL_MIN / 4 && end - mid >= PARALLEL_MIN / 4) {
+			std::future<int> left = std::async(std::launch::async, [&rec, start, mid, depth, base] { return rec(start, mid, depth + 1, base); });
+			r = rec(mid, end, depth + 1, base + 2 * (mid - start) - 1);
+			l = left.get();
+		} else {
+			l = rec(start, mid, depth + 1, base);
+			r = rec(mid, end, depth + 1, base + 2 * (mid - start) - 1);
+		}
+		return put(slot, bounds, l, r);
 	};
-	root = rec(0, n, 0);
+	root = rec(0, n, 0, 0);
 	order = idx;
 	return (int)nodes.size();
 }
@@ -608,6 +624,21 @@ extern "C" int rtb_scene_world_bvh(const rtb_scene* s, rtb_bvh_node* nodes_out, 
 namespace rtb {
 
 namespace {
+// Splits [0, n) over the host threads when the range is large enough to pay for starting them.
+template <typename F>
+void parallel_for(size_t n, F&& body) {
+	const size_t workers = n < 65536 ? 1 : std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency()));
+	if (workers <= 1) { body((size_t)0, n); return; }
+	std::vector<std::thread> pool;
+	const size_t chunk = (n + workers - 1) / workers;
+	for (size_t w = 1; w < workers; ++w) {
+		size_t a = std::min(n, w * chunk), b = std::min(n, a + chunk);
+		if (a < b) pool.emplace_back([&body, a, b] { body(a, b); });
+	}
+	body((size_t)0, std::min(n, chunk));
+	for (std::thread& t : pool) t.join();
+}
+
 struct Flattener {
 	rtb_scene& s;
 	FlatScene& out;
@@ -770,13 +801,26 @@ struct Flattener {
 };
 }  // namespace
 
-int flatten(rtb_scene& s, FlatScene& out) {
+int flatten(rtb_scene& s, FlatScene& out, const GpuBuildContext* gpu) {
 	if (s.root < 0) return fail(RTB_ERR_STATE, "scene has no root object (rtb_scene_set_root)");
+	if (s.world_bvh_mode == RTB_WORLD_BVH_GPU_LBVH && !gpu)
+		return fail(RTB_ERR_STATE, "RTB_WORLD_BVH_GPU_LBVH is built on a renderer's device: use rtb_renderer_set_scene / rtb_renderer_scene_stats");
+	const auto t_start = std::chrono::steady_clock::now();
+	const bool trace = getenv("RTB_LBVH_TRACE") != nullptr;
+	auto t_lap = t_start;
+	auto lap = [&](const char* what) {
+		if (!trace) return;
+		auto t1 = std::chrono::steady_clock::now();
+		fprintf(stderr, "[flatten] %-12s %8.3f ms\n", what, std::chrono::duration<float, std::milli>(t1 - t_lap).count());
+		t_lap = t1;
+	};
 	out = FlatScene();
 	Flattener fl{s, out, {}, {}};
+	fl.items.reserve(s.objects.size()); fl.prim_boxes.reserve(s.objects.size());
 	Xf ident;
 	int rc = fl.walk(s.root, ident, 0);
 	if (rc) return rc;
+	lap("walk");
 	if (fl.items.empty()) return fail(RTB_ERR_INVALID, "scene has no primitives");
 	if (fl.items.size() >= (1u << 26)) return fail(RTB_ERR_UNSUPPORTED, "too many primitives");
 
@@ -788,6 +832,7 @@ int flatten(rtb_scene& s, FlatScene& out) {
 		for (size_t i = 0; i < fl.items.size(); ++i) if (fl.items[i].type == PRIM_MEDIUM_SPHERE || fl.items[i].type == PRIM_MEDIUM_BOX) media.push_back((int)i);
 		std::stable_sort(media.begin(), media.end(), [&](int a, int b) { return surface_area(fl.prim_boxes[a]) > surface_area(fl.prim_boxes[b]); });
 		if (media.size() > 8) media.resize(8);
+		if (!media.empty()) {
 		std::vector<char> is_pre(fl.items.size(), 0);
 		for (int m : media) is_pre[m] = 1;
 		std::vector<Flattener::Item> rest; std::vector<Box3> rest_boxes;
@@ -796,8 +841,10 @@ int flatten(rtb_scene& s, FlatScene& out) {
 			out.pre_list.push_back((int32_t)(((int)out.prims.size() << RTB_LEAF_TYPE_BITS) | it.type));
 			for (int k = 0; k < it.nrec; ++k) { out.prims.push_back(it.rec[k]); out.prim_info.push_back(it.info); out.prim_type.push_back(k == 0 ? it.type : -1); }
 		}
+		rest.reserve(fl.items.size()); rest_boxes.reserve(fl.items.size());
 		for (size_t i = 0; i < fl.items.size(); ++i) if (!is_pre[i]) { rest.push_back(fl.items[i]); rest_boxes.push_back(fl.prim_boxes[i]); }
 		fl.items.swap(rest); fl.prim_boxes.swap(rest_boxes);
+		}
 	}
 	if (fl.items.empty()) {   // nothing but pre-tested media: no BVH at all
 		out.bvh_empty = 1; out.root_ref = 0; out.max_depth_nodes = 0;
@@ -810,32 +857,56 @@ int flatten(rtb_scene& s, FlatScene& out) {
 	const rtbs_object& root = s.objects[s.root];
 	if (!out.bvh_empty) {
 	std::vector<rtb_bvh_node> nodes; std::vector<int> order; int root_idx = -1;
-	const int STACK_LIMIT = 30;
+	const int STACK_LIMIT = RTB_TREE_DEPTH_NORMAL;
 	bool built = false;
+	int depth = 0;
+	lap("media");
+	const auto t_build = std::chrono::steady_clock::now();
 	if (root.kind == RTB_OBJ_BVH && s.world_bvh_mode == RTB_WORLD_BVH_AS_BUILT) {
 		rc = build_bvh(fl.prim_boxes, root.aux, nodes, order, root_idx);
 		if (rc < 0) return rc;
-		built = bvh_depth(nodes, root_idx) <= STACK_LIMIT;
+		depth = bvh_depth(nodes, root_idx);
+		built = depth <= STACK_LIMIT;
+		out.builder = RTB_WORLD_BVH_AS_BUILT;
+	} else if (s.world_bvh_mode == RTB_WORLD_BVH_GPU_LBVH) {
+		rc = build_bvh_lbvh_gpu(fl.prim_boxes, nodes, order, root_idx, *gpu);
+		if (rc < 0) return rc;
+		depth = bvh_depth(nodes, root_idx);
+		built = depth <= RTB_TREE_DEPTH_MAX;
+		out.builder = RTB_WORLD_BVH_GPU_LBVH;
 	}
 	if (!built) {
 		rc = build_bvh_world_sah(fl.prim_boxes, nodes, order, root_idx);
 		if (rc < 0) return rc;
-		if (bvh_depth(nodes, root_idx) > STACK_LIMIT) {
+		out.builder = RTB_WORLD_BVH_QUALITY;
+		depth = bvh_depth(nodes, root_idx);
+		if (depth > STACK_LIMIT) {
 			rc = build_bvh(fl.prim_boxes, RTB_BVH_TOPDOWN_MEDIAN, nodes, order, root_idx);
 			if (rc < 0) return rc;
+			out.builder = RTB_BUILDER_MEDIAN_FALLBACK;
+			depth = bvh_depth(nodes, root_idx);
 		}
 	}
-	out.max_depth_nodes = bvh_depth(nodes, root_idx);
+	out.bvh_build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_build).count();
+	out.max_depth_nodes = depth;
+	out.n_items = (int32_t)order.size();
+	lap("bvh");
 
 	// Lay the records out in BVH leaf order (Factory::hittables, BVH.cu:174-177); a leaf refers to
 	// the first record slot of its item.
 	std::vector<int> slot_of(order.size()), type_of(order.size());
-	for (size_t i = 0; i < order.size(); ++i) {
-		const Flattener::Item& it = fl.items[order[i]];
-		slot_of[i] = (int)out.prims.size(); type_of[i] = it.type;
-		for (int k = 0; k < it.nrec; ++k) { out.prims.push_back(it.rec[k]); out.prim_info.push_back(it.info); out.prim_type.push_back(k == 0 ? it.type : -1); }
+	{
+		size_t slots = out.prims.size();
+		for (size_t i = 0; i < order.size(); ++i) { const Flattener::Item& it = fl.items[order[i]]; slot_of[i] = (int)slots; type_of[i] = it.type; slots += it.nrec; }
+		out.prims.resize(slots); out.prim_info.resize(slots); out.prim_type.resize(slots);
 	}
-	s.world_nodes = nodes; s.world_root = root_idx;
+	parallel_for(order.size(), [&](size_t a, size_t b) {
+		for (size_t i = a; i < b; ++i) {
+			const Flattener::Item& it = fl.items[order[i]];
+			for (int k = 0; k < it.nrec; ++k) { out.prims[slot_of[i] + k] = it.rec[k]; out.prim_info[slot_of[i] + k] = it.info; out.prim_type[slot_of[i] + k] = k == 0 ? it.type : -1; }
+		}
+	});
+	lap("layout");
 
 	// Wide layout: one 64-byte record per inner node carrying both children's boxes, numbered in
 	// depth-first pre-order (root = 0) so the near part of a subtree is contiguous.
@@ -855,7 +926,9 @@ int flatten(rtb_scene& s, FlatScene& out) {
 		}
 		out.nodes.resize(inner_order.size());
 		auto ref_of = [&](int i) { return nodes[i].left_child_idx == -1 ? leaf_ref(i) : dev_index[i]; };
-		for (int i : inner_order) {
+		parallel_for(inner_order.size(), [&](size_t a, size_t b) {
+		for (size_t at = a; at < b; ++at) {
+			const int i = inner_order[at];
 			const rtb_bvh_node& l = nodes[nodes[i].left_child_idx];
 			const rtb_bvh_node& r = nodes[nodes[i].right_child_hittable_idx];
 			DevNode& d = out.nodes[dev_index[i]];
@@ -873,11 +946,14 @@ int flatten(rtb_scene& s, FlatScene& out) {
 			put_box(d.f, l); put_box(d.f + 6, r);
 			d.left = ref_of(nodes[i].left_child_idx); d.right = ref_of(nodes[i].right_child_hittable_idx); d.pad0 = d.pad1 = 0;
 		}
+		});
 		out.root_ref = 0;
 	}
+	s.world_nodes = std::move(nodes); s.world_root = root_idx;
 
 	}
 
+	lap("wide");
 	// Materials / textures.
 	out.materials.resize(s.materials.size());
 	for (size_t i = 0; i < s.materials.size(); ++i) {
@@ -896,6 +972,7 @@ int flatten(rtb_scene& s, FlatScene& out) {
 	out.blob = s.blob;
 	out.background_mode = s.background_mode;
 	memcpy(out.background, s.background, 12);
+	out.flatten_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_start).count();
 	return RTB_OK;
 }
 

@@ -42,8 +42,18 @@ int build_bvh_world_sah(const std::vector<Box3>& boxes, std::vector<rtb_bvh_node
                         std::vector<int>& order, int& root);
 int bvh_depth(const std::vector<rtb_bvh_node>& nodes, int root);
 
+// Where RTB_WORLD_BVH_GPU_LBVH builds: the renderer's device and stream, and two grow-only scratch buffers the
+// renderer keeps between builds (device memory; pinned host memory for the download), so that a rebuild allocates nothing.
+struct GpuScratch { void* device = nullptr; size_t device_bytes = 0; void* pinned = nullptr; size_t pinned_bytes = 0; };
+struct GpuBuildContext { int device; void* stream; GpuScratch* scratch; };
+
+// GPU linear BVH (rtb_lbvh.cu): same outputs as build_bvh; inner nodes 0..n-2 (root 0), leaf of sorted position k = n-1+k.
+int build_bvh_lbvh_gpu(const std::vector<Box3>& boxes, std::vector<rtb_bvh_node>& nodes, std::vector<int>& order,
+                       int& root, const GpuBuildContext& gpu);
+void free_gpu_scratch(GpuScratch& scratch);
+
 // Flattens the object graph to world-space primitives + one world BVH.
-int flatten(rtb_scene& s, FlatScene& out);
+int flatten(rtb_scene& s, FlatScene& out, const GpuBuildContext* gpu = nullptr);
 
 }  // namespace rtb
 #endif

@@ -18,6 +18,10 @@ enum PrimType : int {
 	PRIM_XF = 8
 };
 #define RTB_LEAF_TYPE_BITS 4
+// Deepest world BVH the kernels walk: 30 levels on the 32-entry stack (16 entries when <= 17), up to 62 on the
+// 64-entry stack that only the GPU linear BVH of a large scene needs.
+#define RTB_TREE_DEPTH_NORMAL 30
+#define RTB_TREE_DEPTH_MAX 62
 
 // Child reference of a wide-layout BVH node: >= 0 inner node index; < 0 leaf,
 // ~ref = (prim_index << 4) | PrimType.
@@ -66,6 +70,9 @@ struct FlatScene {
 	int32_t background_mode = 0;
 	float background[3] = {0, 0, 0};
 	int32_t max_depth_nodes = 0;         // tree depth (stack bound check)
+	int32_t builder = 0;                 // rtb_world_bvh_mode that produced the tree (3 = median fallback)
+	int32_t n_items = 0;                 // BVH leaves
+	float flatten_ms = 0.0f, bvh_build_ms = 0.0f;
 };
 
 }  // namespace rtb

@@ -201,3 +201,14 @@ int main(int, char** argv) {
     assert len(tris) == 3 and objs[int(h["root_object"])]["kind"] == 6 and len(children) == 3
     got = sorted(tuple(np.round(t["f"][:9], 6)) for t in tris)          # Q, u, v
     assert got == sorted([(0, 0, 0, 1, 0, 0, 1, 1, 0), (0, 0, 0, 1, 1, 0, 0, 1, 0), (0, 0, 1, 0, 0, -1, 1, 0, -1)])
+
+
+def test_gpu_lbvh_mode_needs_a_renderer(rtb):
+    """RTB_WORLD_BVH_GPU_LBVH is built on a device; the host-only flatten refuses it instead of building something else."""
+    s = rtb.Scene.named("book2_bouncing"); s.set_world_bvh(rtb.WORLD_BVH_GPU_LBVH)
+    with pytest.raises(rtb.RtbError, match="GPU_LBVH"):
+        s.flatten_stats()
+    with pytest.raises(rtb.RtbError):
+        s.set_world_bvh(7)
+    s.set_world_bvh(rtb.WORLD_BVH_QUALITY)
+    assert s.flatten_stats()["primitives"] == 488

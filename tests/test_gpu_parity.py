@@ -233,6 +233,86 @@ def test_cli_app_matches_the_library(rtb, renderer, tmp_path):
     assert np.array_equal(img, ref)
 
 
+def _check_tree(nodes, root, n_prims):
+    """Structure of a world BVH in the reference node layout: 2n-1 nodes, every primitive in exactly one leaf,
+    every inner box the exact union of its children's."""
+    assert len(nodes) == 2 * n_prims - 1
+    leaf = nodes["left_child_idx"] == -1
+    assert sorted(nodes["right_child_hittable_idx"][leaf].tolist()) == list(range(n_prims))
+    inner = np.nonzero(~leaf)[0]
+    l = nodes[nodes["left_child_idx"][inner]]; r = nodes[nodes["right_child_hittable_idx"][inner]]
+    assert np.array_equal(nodes["bmin"][inner], np.minimum(l["bmin"], r["bmin"]))
+    assert np.array_equal(nodes["bmax"][inner], np.maximum(l["bmax"], r["bmax"]))
+    seen = np.zeros(len(nodes), dtype=np.int32)           # a tree: every node but the root has exactly one parent
+    np.add.at(seen, nodes["left_child_idx"][inner], 1); np.add.at(seen, nodes["right_child_hittable_idx"][inner], 1)
+    assert seen[root] == 0 and (np.delete(seen, root) == 1).all()
+
+
+@pytest.mark.parametrize("name,lo,hi", [("book2_bouncing", -12, 12), ("book2_final", -200, 600), ("mesh_icospheres", -4, 4), ("book2_cornell_smoke", 0, 555)])
+def test_gpu_lbvh_world_bvh(rtb, orc, renderer, name, lo, hi):
+    """RTB_WORLD_BVH_GPU_LBVH: the tree built on the device (Morton codes, radix sort, one-pass hierarchy, bottom-up
+    fit) is a valid BVH over the same primitives, and closest hits through it are bit-identical to the oracle's
+    (which walks the scene graph as the reference would)."""
+    scene = rtb.Scene.named(name)
+    scene.set_world_bvh(rtb.WORLD_BVH_GPU_LBVH)
+    renderer.set_scene(scene)
+    st = renderer.scene_stats()
+    assert st["builder"] == "gpu_lbvh" and st["depth"] <= 30
+    nodes, root = scene.world_bvh()
+    _check_tree(nodes, root, st["primitives"])
+    rays = np.concatenate([camera_rays(rtb, scene.info.camera, 160, 160, "renderer"), random_rays(rtb, 100_000, lo, hi, seed=5)])
+    if name != "book2_cornell_smoke":                       # (a medium's hit distance is random: the image below covers that scene)
+        g = renderer.trace_rays(rays)
+        o = _oracle_scene(orc, scene).trace_rays(rays, rtb.HIT_DTYPE)
+        assert _compare_hits(rtb, g, o, exact=True) > 10_000
+    # and the same image, path for path
+    cam = scene.info.camera; renderer.set_camera(cam)
+    renderer.render(96, 96, 0, 4, 20, seed=1984); gpu = renderer.download_accum()
+    ref, _, _ = _oracle_scene(orc, scene).render(cam, 96, 96, 0, 4, 20, seed=1984)
+    diff = np.abs(gpu[..., :3] - ref[..., :3]).max(axis=2)
+    assert float((diff > 1e-4 * np.maximum(np.abs(ref[..., :3]).max(axis=2), 1.0)).mean()) <= 0.02
+
+
+def test_gpu_lbvh_degenerate_inputs(rtb, orc, renderer):
+    """One primitive, two primitives, and many primitives with identical boxes (equal Morton codes are split by
+    sorted position; a run that would make the tree deeper than the traversal stack falls back to the host builder)."""
+    for count, same in [(1, False), (2, False), (3, False), (700, True), (5000, True)]:
+        s = rtb.Scene(); m = s.lambertian(albedo=(0.5, 0.5, 0.5))
+        ids = [s.sphere((1.0, 2.0, 3.0) if same else (2.5 * k, 0.0, 0.0), 0.5 + (0.001 * k if same else 0.0), m) for k in range(count)]
+        s.set_root(s.list(ids)); s.set_world_bvh(rtb.WORLD_BVH_GPU_LBVH)
+        renderer.set_scene(s)
+        st = renderer.scene_stats()
+        assert st["primitives"] == count and st["depth"] <= 30 and st["builder"] in ("gpu_lbvh", "host_sah", "host_median_fallback")
+        if count <= 700:
+            assert st["builder"] == "gpu_lbvh"
+        nodes, root = s.world_bvh(); _check_tree(nodes, root, count)
+        rays = random_rays(rtb, 20_000, -6, 9, seed=count)
+        g = renderer.trace_rays(rays); o = _oracle_scene(orc, s).trace_rays(rays, rtb.HIT_DTYPE)
+        _compare_hits(rtb, g, o, exact=True)
+
+
+def test_gpu_lbvh_deep_tree_uses_the_deep_stack(rtb, orc, renderer):
+    """A linear BVH can be much deeper than a SAH tree: centres at 1000 * 2^-k peel off one Morton bit per level,
+    and 4,000 primitives sharing one cell add their own levels.  Past 30 levels the kernels switch to the 64-entry
+    stack; hits and the image stay identical to the oracle's."""
+    s = rtb.Scene(); m = s.lambertian(albedo=(0.5, 0.5, 0.5)); g = s.dielectric(1.5)
+    ids = [s.sphere((1000.0 * 2.0 ** -k, 0.0, 0.0), 0.2 * 1000.0 * 2.0 ** -k, m if k % 2 else g) for k in range(21)]
+    ids += [s.sphere((0.0, 0.0, 0.0), 0.05 * (1 + k / 4000.0), m) for k in range(4000)]
+    s.set_root(s.list(ids)); s.set_world_bvh(rtb.WORLD_BVH_GPU_LBVH)
+    renderer.set_scene(s)
+    st = renderer.scene_stats()
+    assert st["builder"] == "gpu_lbvh" and 30 < st["depth"] <= 62, st
+    nodes, root = s.world_bvh(); _check_tree(nodes, root, len(ids))
+    cam = rtb.make_camera("pinhole", (400, 300, 900), (300, 0, 0), (0, 1, 0), 60.0, 1.0)
+    rays = np.concatenate([camera_rays(rtb, cam, 128, 128, "renderer"), random_rays(rtb, 20_000, -50, 1100, seed=3), random_rays(rtb, 10_000, -3, 3, seed=4)])
+    rays["d"][-10_000:] = -rays["o"][-10_000:] + rays["d"][-10_000:] * np.float32(0.01)   # the last third aims at the crowded cell
+    g_hits = renderer.trace_rays(rays); o = _oracle_scene(orc, s); o_hits = o.trace_rays(rays, rtb.HIT_DTYPE)
+    assert _compare_hits(rtb, g_hits, o_hits, exact=True) > 5_000
+    renderer.set_camera(cam); renderer.render(64, 64, 0, 4, 12, seed=5); gpu = renderer.download_accum()
+    ref, _, _ = o.render(cam, 64, 64, 0, 4, 12, seed=5)
+    np.testing.assert_allclose(gpu[..., :3], ref[..., :3], rtol=1e-4, atol=1e-4)
+
+
 def test_cli_app_renders_an_obj_mesh(tmp_path):
     """rtb_app --obj: MeshHandle::LoadObj -> MakeMesh -> HittableList -> Renderer::MakeRenderer.  An octahedron of grey
     clay on the checkered floor under the sky: the centre of the image is the mesh (grey, r == g == b up to noise),
