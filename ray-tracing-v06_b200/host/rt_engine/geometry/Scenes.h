@@ -6,39 +6,40 @@
 
 #include "rtb.h"
 
-class aabb;
-class Hittable;
-class cuHostRND;
-class BVH_Handle;
-class SphereHandle;
+class aabb; class BVH_Handle; class cuHostRND; class Hittable; class SphereHandle;
 
+// The scene object FirstApp keeps alive while rendering: it owns the sphere handles (and through them the
+// materials), the BVH handle and the world bounds.  Built only by its Factory; move-only.
 class SceneBook2BVH {
-	SceneBook2BVH();
-	void _delete();
-	BVH_Handle* bvh;
-	aabb* world_bounds;
-	std::vector<SphereHandle> sphere_handles;
-
 public:
-	~SceneBook2BVH();
+	class Factory;
 	SceneBook2BVH(SceneBook2BVH&& scene);
 	SceneBook2BVH& operator=(SceneBook2BVH&& scene);
-	class Factory;
-	const Hittable* getWorldPtr() const;
+	~SceneBook2BVH();
+	const Hittable* getWorldPtr() const;   // what Renderer::MakeRenderer takes as d_world_ptr
+
+private:
+	SceneBook2BVH();
+	void _delete();
+	BVH_Handle* bvh; aabb* world_bounds;              // (declaration order = initialisation order of the constructors)
+	std::vector<SphereHandle> sphere_handles;
 };
 
+// Draws the 22 x 22 grid of random spheres from a host generator (cuHostRND(512, 1984)) and hands the finished
+// world over: Factory{}.MakeScene() is the whole public protocol (FirstApp.cpp:34-35).
 class SceneBook2BVH::Factory {
-	void _delete();
-	void _populate_world();
-	cuHostRND* host_rnd;
-	std::vector<SphereHandle> sphere_handles;
-
 public:
 	Factory();
-	~Factory();
 	Factory(Factory&& factory);
 	Factory& operator=(Factory&& factory);
+	~Factory();
 	SceneBook2BVH* MakeScene();
+
+private:
+	void _populate_world();
+	void _delete();
+	cuHostRND* host_rnd;
+	std::vector<SphereHandle> sphere_handles;
 };
 
 // ---- C accessors used by the Python tests / bench (exported from librtb200_scenes.so)
