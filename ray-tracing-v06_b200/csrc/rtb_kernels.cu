@@ -307,6 +307,10 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 	const float ny = d.y < 0.0f ? idy : 0.0f, fy = d.y < 0.0f ? 0.0f : idy;
 	const float nz = d.z < 0.0f ? idz : 0.0f, fz = d.z < 0.0f ? 0.0f : idz;
 
+#if RTB_NODE_PAIRED
+	const float2 id_xy = make_float2(idx, idy), oi_xy = make_float2(oix, oiy), n_xy = make_float2(nx, ny), f_xy = make_float2(fx, fy);
+	const float2 id_zz = make_float2(idz, idz), oi_zz = make_float2(oiz, oiz), n_zz = make_float2(nz, nz), f_zz = make_float2(fz, fz);
+#endif
 	int cur = sv.root_ref;
 	int sp = 0;
 	int n_inner = 0, n_leaf = 0;   // STATS only
@@ -318,12 +322,27 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 			const float4* np = sv.nodes + 4 * (size_t)cur;
 			const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2);
 			const int2 n3 = __ldg(reinterpret_cast<const int2*>(np + 3));
+#if RTB_NODE_PAIRED
+			// the same 18 fused multiply-adds, two per instruction (FFMA2): x and y of one child share an instruction,
+			// z of the two children share one; every component is an IEEE fma, so the results are the bits of the scalar form
+			const float2 l_xy = __ffma2_rn(make_float2(n0.x, n0.y), id_xy, oi_xy);
+			const float2 r_xy = __ffma2_rn(make_float2(n1.x, n1.y), id_xy, oi_xy);
+			const float2 lr_z = __ffma2_rn(make_float2(n2.x, n2.y), id_zz, oi_zz);
+			const float2 ln_xy = __ffma2_rn(make_float2(n0.z, n0.w), n_xy, l_xy), lf_xy = __ffma2_rn(make_float2(n0.z, n0.w), f_xy, l_xy);
+			const float2 rn_xy = __ffma2_rn(make_float2(n1.z, n1.w), n_xy, r_xy), rf_xy = __ffma2_rn(make_float2(n1.z, n1.w), f_xy, r_xy);
+			const float2 lrn_z = __ffma2_rn(make_float2(n2.z, n2.w), n_zz, lr_z), lrf_z = __ffma2_rn(make_float2(n2.z, n2.w), f_zz, lr_z);
+			const float ltmin = fmaxf(fmaxf(ln_xy.x, ln_xy.y), lrn_z.x);
+			const float ltmax = fminf(fminf(lf_xy.x, lf_xy.y), lrf_z.x);
+			const float rtmin = fmaxf(fmaxf(rn_xy.x, rn_xy.y), lrn_z.y);
+			const float rtmax = fminf(fminf(rf_xy.x, rf_xy.y), lrf_z.y);
+#else
 			const float lx = fmaf(n0.x, idx, oix), ly = fmaf(n0.y, idy, oiy), lz = fmaf(n0.z, idz, oiz);
 			const float rx = fmaf(n1.z, idx, oix), ry = fmaf(n1.w, idy, oiy), rz = fmaf(n2.x, idz, oiz);
 			const float ltmin = fmaxf(fmaxf(fmaf(n0.w, nx, lx), fmaf(n1.x, ny, ly)), fmaf(n1.y, nz, lz));
 			const float ltmax = fminf(fminf(fmaf(n0.w, fx, lx), fmaf(n1.x, fy, ly)), fmaf(n1.y, fz, lz));
 			const float rtmin = fmaxf(fmaxf(fmaf(n2.y, nx, rx), fmaf(n2.z, ny, ry)), fmaf(n2.w, nz, rz));
 			const float rtmax = fminf(fminf(fmaf(n2.y, fx, rx), fmaf(n2.z, fy, ry)), fmaf(n2.w, fz, rz));
+#endif
 			// aabb::intersects: tmin <= tmax && tmin < ray_max && tmax > 0   aabb.cuh:41
 			const bool hl = ltmin <= ltmax && ltmin < tbest && ltmax > 0.0f;
 			const bool hr = rtmin <= rtmax && rtmin < tbest && rtmax > 0.0f;

@@ -943,7 +943,14 @@ int flatten(rtb_scene& s, FlatScene& out, const GpuBuildContext* gpu) {
 					f[k] = mn; f[3 + k] = ext;
 				}
 			};
+#if RTB_NODE_PAIRED
+			float lb[6], rb[6]; put_box(lb, l); put_box(rb, r);
+			d.f[0] = lb[0]; d.f[1] = lb[1]; d.f[2] = lb[3]; d.f[3] = lb[4];
+			d.f[4] = rb[0]; d.f[5] = rb[1]; d.f[6] = rb[3]; d.f[7] = rb[4];
+			d.f[8] = lb[2]; d.f[9] = rb[2]; d.f[10] = lb[5]; d.f[11] = rb[5];
+#else
 			put_box(d.f, l); put_box(d.f + 6, r);
+#endif
 			d.left = ref_of(nodes[i].left_child_idx); d.right = ref_of(nodes[i].right_child_hittable_idx); d.pad0 = d.pad1 = 0;
 		}
 		});

@@ -20,6 +20,12 @@ enum PrimType : int {
 #define RTB_LEAF_TYPE_BITS 4
 // Deepest world BVH the kernels walk: 30 levels on the 32-entry stack (16 entries when <= 17), up to 62 on the
 // 64-entry stack that only the GPU linear BVH of a large scene needs.
+// Wide-node float layout.  0: (Lmin.xyz, Lext.xyz, Rmin.xyz, Rext.xyz).  1: paired for the packed two-wide FMA of
+// sm_100 (FFMA2): (Lmin.xy, Lext.xy | Rmin.xy, Rext.xy | Lmin.z, Rmin.z, Lext.z, Rext.z), so that every operand pair of
+// the slab test is an aligned register pair of one 16-byte load.
+#ifndef RTB_NODE_PAIRED
+#define RTB_NODE_PAIRED 1
+#endif
 #define RTB_TREE_DEPTH_NORMAL 30
 #define RTB_TREE_DEPTH_MAX 62
 

@@ -9,6 +9,7 @@ NV="/usr/local/cuda/bin/nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_1
 $NV -x cu -c csrc/rtb_scene.cpp -o build/var_$name/rtb_scene.o &
 $NV -c csrc/rtb_kernels.cu -o build/var_$name/rtb_kernels.o &
 $NV -c csrc/rtb_render.cu -o build/var_$name/rtb_render.o &
+$NV -c csrc/rtb_lbvh.cu -o build/var_$name/rtb_lbvh.o &
 wait
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/$name.so build/var_$name/*.o -cudart static
 echo built variants/$name.so
