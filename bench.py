@@ -129,7 +129,10 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
+
+
+_JSON_OUT = sys.stdout
 
 
 def main():
@@ -150,6 +153,12 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", os.environ.get("MASTER_PORT", "29533"), __file__] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    # Exactly ONE line goes to stdout (the JSON line, rank 0): everything libraries print on fd 1 meanwhile (NCCL's
+    # version banner, subprocess chatter) is sent to stderr, and the line is written to the saved descriptor at the end.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
@@ -307,7 +316,7 @@ def main():
             "cpu_baseline": cpu, "psnr_vs_oracle_db": psnr_db,
             "reference_gpu": refgpu,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
