@@ -39,6 +39,20 @@ using rt::v3;
 __device__ __forceinline__ v3 xyz(const float4& f) { return rt::mk(f.x, f.y, f.z); }
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+// Two consecutive float4 (32 bytes, 32-byte aligned).  sm_100 has 256-bit global loads (LDG.E.256): with
+// -DRTB_LDG256=1 a 64-byte node is two requests instead of four.  Measured neutral on B200 (traverse 30.1 vs 29.9 ms
+// per step, profiles/r1_experiments.md), so the default stays with 128-bit loads.
+#ifndef RTB_LDG256
+#define RTB_LDG256 0
+#endif
+__device__ __forceinline__ void ldg8(const float4* p, float4& a, float4& b) {
+#if RTB_LDG256
+	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	    : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#else
+	a = __ldg(p); b = __ldg(p + 1);
+#endif
+}
 
 // Path id -> (global pixel index, absolute sample index).  Paths of a batch are laid out
 // sample-major: id = local_sample * npix + local_pixel, local pixels row-major from row_begin.
@@ -134,7 +148,8 @@ __device__ __forceinline__ float sphere_closest(v3 o, v3 d, float a, v3 c, float
 
 // Book quad::hit / triangle with the reference's t policy (t >= 0, strictly closer than the best).
 __device__ __forceinline__ float planar_hit(v3 o, v3 d, const float4* pp, float4 q0, bool tri, float tbest) {
-	float4 q1 = ldg4(pp + 1), q2 = ldg4(pp + 2), q3 = ldg4(pp + 3);
+	float4 q1 = ldg4(pp + 1), q2, q3;
+	ldg8(pp + 2, q2, q3);
 	v3 N = rt::mk(q1.w, q2.w, q3.w);
 	float denom = rt::dot(N, d);
 	if (fabsf(denom) < 1e-8f) return FLT_MAX;
@@ -320,8 +335,9 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 		while (cur >= 0) {
 			if (STATS) ++n_inner;
 			const float4* np = sv.nodes + 4 * (size_t)cur;
-			const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2);
-			const int2 n3 = __ldg(reinterpret_cast<const int2*>(np + 3));
+			float4 n0, n1, n2, n3f;
+			ldg8(np, n0, n1); ldg8(np + 2, n2, n3f);
+			const int2 n3 = make_int2(__float_as_int(n3f.x), __float_as_int(n3f.y));
 #if RTB_NODE_PAIRED
 			// the same 18 fused multiply-adds, two per instruction (FFMA2): x and y of one child share an instruction,
 			// z of the two children share one; every component is an IEEE fma, so the results are the bits of the scalar form
