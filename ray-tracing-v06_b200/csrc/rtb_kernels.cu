@@ -165,6 +165,48 @@ __device__ __forceinline__ float planar_hit(v3 o, v3 d, const float4* pp, float4
 	return t;
 }
 
+// A book box() is six quads.  One BVH leaf holds a (min, max) record followed by the six ordinary quad records; a slab
+// test on (min, max) only SELECTS which faces the ray can meet (the entry faces, then the exit faces, with a tolerance
+// far above the rounding of either computation, in list order), and the hit itself is the exact quad test on those
+// records - so the result is the one testing all six quads gives, and it is reported on the quad (`face_code`).
+//   rec_stride = float4s from one record to the next (4, or 8 when every record is followed by its transform).
+__device__ __forceinline__ float box_hit(v3 o, v3 d, float idx, float idy, float idz, float oix, float oiy, float oiz,
+                                         const float4* pp, float4 q0, int rec_stride, float tbest, int& face) {
+	const float4 q1 = ldg4(pp + 1);                         // q0 = (min.xyz, max.x), q1 = (max.y, max.z, -, -)
+	const float ax = fmaf(q0.x, idx, oix), bx = fmaf(q0.w, idx, oix);
+	const float ay = fmaf(q0.y, idy, oiy), by = fmaf(q1.x, idy, oiy);
+	const float az = fmaf(q0.z, idz, oiz), bz = fmaf(q1.y, idz, oiz);
+	const float t0x = fminf(ax, bx), t1x = fmaxf(ax, bx), t0y = fminf(ay, by), t1y = fmaxf(ay, by), t0z = fminf(az, bz), t1z = fmaxf(az, bz);
+	const float tenter = fmaxf(fmaxf(t0x, t0y), t0z), texit = fminf(fminf(t1x, t1y), t1z);
+	const float scale = fmaxf(fmaxf(fmaxf(fabsf(oix), fabsf(oiy)), fabsf(oiz)), fmaxf(fabsf(tenter), fabsf(texit)));
+	const float tol = 2e-5f * scale;
+	face = -1;
+	if (tenter > texit + tol || texit < -tol || tenter - tol >= tbest) return FLT_MAX;
+	// faces in list order: 0 front (z max), 1 right (x max), 2 back (z min), 3 left (x min), 4 top (y max), 5 bottom (y min)
+	const int nfx = ax <= bx ? 3 : 1, nfy = ay <= by ? 5 : 4, nfz = az <= bz ? 2 : 0;
+	unsigned entry = 0, exits = 0;
+	if (t0x >= tenter - tol) entry |= 1u << nfx;
+	if (t0y >= tenter - tol) entry |= 1u << nfy;
+	if (t0z >= tenter - tol) entry |= 1u << nfz;
+	if (t1x <= texit + tol) exits |= 1u << (4 - nfx);       // the opposite face: 3 <-> 1
+	if (t1y <= texit + tol) exits |= 1u << (9 - nfy);       // 5 <-> 4
+	if (t1z <= texit + tol) exits |= 1u << (2 - nfz);       // 2 <-> 0
+	unsigned mask = tenter >= -tol ? entry : 0u;
+	if (texit - tenter <= tol) mask |= exits;                // paper-thin along the ray: the order of entry and exit is not reliable
+	float best = FLT_MAX;
+	for (int pass = 0; pass < 2; ++pass) {
+		for (unsigned m = mask; m; m &= m - 1) {
+			const int f = __ffs(m) - 1;
+			const float4* fp = pp + rec_stride * (1 + f);
+			const float t = planar_hit(o, d, fp, ldg4(fp), false, fminf(tbest, best));
+			if (t < best) { best = t; face = f; }
+		}
+		if (best < FLT_MAX) break;
+		mask = exits & ~mask;
+	}
+	return best;
+}
+
 // Free-flight uniforms of the media a ray meets.  Medium m of a path segment uses component (m & 3)
 // of Philox(seed, pixel; sample, bounce, STREAM_MEDIUM0 + (m >> 2)); the block is generated lazily,
 // only when some medium's boundary interval survives the geometric rejections, and shared by up to
@@ -229,7 +271,7 @@ __device__ __forceinline__ float medium_box_hit(v3 o, v3 d, float a, float4 q0, 
 }
 
 // Instances.  T = (cos, sin, off.x, off.y), (off.z, -, -, -) with world = R_y(theta) * object + off.
-__device__ __forceinline__ int xf_offset(int base) { return base == PRIM_SPHERE ? 1 : (base == PRIM_MOVING_SPHERE ? 2 : 4); }
+__device__ __forceinline__ int xf_offset(int base) { return base == PRIM_SPHERE ? 1 : (base == PRIM_MOVING_SPHERE ? 2 : 4); }   // quads, triangles, boxes: the next record
 
 // world ray -> object ray: origin - offset (book translate::hit), then rotate by -theta (book rotate_y::hit)
 __device__ __forceinline__ void xf_ray(const float4* tp, v3 o, v3 d, v3& oo, v3& dd) {
@@ -253,8 +295,13 @@ __device__ __forceinline__ v3 xf_vec_to_world(const float4* tp, v3 v) {
 
 
 // One primitive against one ray: the t of the hit if it is closer than tbest, else FLT_MAX.
+// `hit_code` is what a hit is reported on: the leaf itself, or for a box the quad record of the face that was hit.
+// (idx.. oiz: the ray's slab-test reciprocals, used to pick the faces of a box.)
+struct RaySlab { float idx, idy, idz, oix, oiy, oiz; };
 template <bool MEDIA>
-__device__ __forceinline__ float leaf_test(const SceneView& sv, int code, v3 o, v3 d, float a, float time, MediumRng& mr, float tbest) {
+__device__ __forceinline__ float leaf_test(const SceneView& sv, int code, v3 o, v3 d, float a, float time, MediumRng& mr, float tbest,
+                                           const RaySlab& rs, int& hit_code) {
+	hit_code = code;
 	const int type = code & 15;
 	const float4* pp = sv.prims + 4 * (size_t)(code >> RTB_LEAF_TYPE_BITS);
 	const float4 q0 = ldg4(pp);
@@ -267,6 +314,10 @@ __device__ __forceinline__ float leaf_test(const SceneView& sv, int code, v3 o, 
 		t = sphere_closest(o, d, a, rt::mix(xyz(q0), xyz(q1), time), q0.w);
 	} else if (type == PRIM_QUAD || type == PRIM_TRIANGLE) {
 		t = planar_hit(o, d, pp, q0, type == PRIM_TRIANGLE, tbest);
+	} else if (type == PRIM_BOX) {
+		int face;
+		t = box_hit(o, d, rs.idx, rs.idy, rs.idz, rs.oix, rs.oiy, rs.oiz, pp, q0, 4, tbest, face);
+		if (face >= 0) hit_code = (((code >> RTB_LEAF_TYPE_BITS) + 1 + face) << RTB_LEAF_TYPE_BITS) | PRIM_QUAD;
 	} else if (type & PRIM_XF) {
 		// instance: take the ray into the primitive's frame (book translate::hit, rotate_y::hit)
 		const int base = type & 7;
@@ -275,6 +326,16 @@ __device__ __forceinline__ float leaf_test(const SceneView& sv, int code, v3 o, 
 		const float a2 = rt::dot(dd, dd);
 		if (base == PRIM_SPHERE) t = sphere_closest(oo, dd, a2, xyz(q0), q0.w);
 		else if (base == PRIM_MOVING_SPHERE) t = sphere_closest(oo, dd, a2, rt::mix(xyz(q0), xyz(ldg4(pp + 1)), time), q0.w);
+		else if (base == PRIM_BOX) {
+			// the box in its own frame; every record (the box's and each face's) is followed by the transform
+			const float gx = fabsf(dd.x) < 1e-20f ? copysignf(1e-20f, dd.x) : dd.x;
+			const float gy = fabsf(dd.y) < 1e-20f ? copysignf(1e-20f, dd.y) : dd.y;
+			const float gz = fabsf(dd.z) < 1e-20f ? copysignf(1e-20f, dd.z) : dd.z;
+			const float jx = __frcp_rn(gx), jy = __frcp_rn(gy), jz = __frcp_rn(gz);
+			int face;
+			t = box_hit(oo, dd, jx, jy, jz, -(oo.x * jx), -(oo.y * jy), -(oo.z * jz), pp, q0, 8, tbest, face);
+			if (face >= 0) hit_code = (((code >> RTB_LEAF_TYPE_BITS) + 2 * (1 + face)) << RTB_LEAF_TYPE_BITS) | PRIM_QUAD | PRIM_XF;
+		}
 		else t = planar_hit(oo, dd, pp, q0, base == PRIM_TRIANGLE, tbest);
 	} else if (MEDIA) {
 		const float4 q1 = ldg4(pp + 1);
@@ -304,8 +365,9 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 	if (MEDIA) {   // media first: a scatter inside a medium bounds the BVH walk tightly
 		for (int k = 0; k < sv.n_pre; ++k) {
 			const int code = __ldg(sv.pre_list + k);
-			const float t = leaf_test<true>(sv, code, o, d, a, time, mr, tbest);
-			if (t < tbest) { tbest = t; best = code; }
+			int hit_code;
+			const float t = leaf_test<true>(sv, code, o, d, a, time, mr, tbest, RaySlab{}, hit_code);   // (media only: no slab data needed)
+			if (t < tbest) { tbest = t; best = hit_code; }
 		}
 		if (sv.bvh_empty) { tbest_out = tbest; code_out = best; return; }
 	}
@@ -381,8 +443,9 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 		if (cur < 0) {
 			if (STATS) ++n_leaf;
 			const int code = ~cur;
-			const float t = leaf_test<(MEDIA == 2)>(sv, code, o, d, a, time, mr, tbest);
-			if (t < tbest) { tbest = t; best = code; }   // "if (t >= rec.distance) return false"  SphereHittable.cu:58
+			int hit_code;
+			const float t = leaf_test<(MEDIA == 2)>(sv, code, o, d, a, time, mr, tbest, RaySlab{idx, idy, idz, oix, oiy, oiz}, hit_code);
+			if (t < tbest) { tbest = t; best = hit_code; }   // "if (t >= rec.distance) return false"  SphereHittable.cu:58
 			if (sp == 0) break;
 			--sp; cur = stack[sp * TRAVERSE_THREADS];
 		}

@@ -643,13 +643,18 @@ struct Flattener {
 	rtb_scene& s;
 	FlatScene& out;
 	// One item per logical primitive (= one BVH leaf); an item owns one or two 64-byte record slots.
-	struct Item { DevPrim rec[2]; int nrec; int type; DevPrimInfo info; };
+	// Records live in one pool; rec_type tags the first slot of everything a hit can name (-1 = continuation slot).
+	struct Item { int first; int nrec; int type; DevPrimInfo info; };
 	std::vector<Item> items;
 	std::vector<Box3> prim_boxes;
+	std::vector<DevPrim> recs;
+	std::vector<int> rec_type;
+	bool box_as_quads = false;   // RTB_BOX_AS_QUADS=1: a box is six independent BVH leaves (the layout before PRIM_BOX)
 
 	void emit(int type, const DevPrim& p, const Box3& b, int mat, int obj, const DevPrim* second = nullptr) {
-		Item it{}; it.rec[0] = p; it.nrec = 1; it.type = type; it.info.material = mat; it.info.object = obj;
-		if (second) { it.rec[1] = *second; it.nrec = 2; }
+		Item it{}; it.first = (int)recs.size(); it.nrec = 1; it.type = type; it.info.material = mat; it.info.object = obj;
+		recs.push_back(p); rec_type.push_back(type);
+		if (second) { recs.push_back(*second); rec_type.push_back(-1); it.nrec = 2; }
 		items.push_back(it);
 		prim_boxes.push_back(b);
 	}
@@ -697,8 +702,8 @@ struct Flattener {
 			emit(PRIM_MOVING_SPHERE | PRIM_XF, p, b, o.mat, id);
 		}
 	}
-	void emit_planar(int type, const float Q[3], const float u[3], const float v[3], int mat, int id, const Xf& x) {
-		// book quad ctor, in the primitive's own frame: n = cross(u,v); normal = unit(n); D = dot(normal,Q); w = n / dot(n,n)
+	// book quad ctor, in the primitive's own frame: n = cross(u,v); normal = unit(n); D = dot(normal,Q); w = n / dot(n,n)
+	static DevPrim planar_record(const float Q[3], const float u[3], const float v[3]) {
 		rt::v3 U = rt::mk(u[0], u[1], u[2]), V = rt::mk(v[0], v[1], v[2]), QQ = rt::mk(Q[0], Q[1], Q[2]);
 		rt::v3 n = rt::cross(U, V);
 		rt::v3 N = rt::normalize(n);
@@ -709,16 +714,24 @@ struct Flattener {
 		p.q[4] = u[0]; p.q[5] = u[1]; p.q[6] = u[2]; p.q[7] = N.x;
 		p.q[8] = v[0]; p.q[9] = v[1]; p.q[10] = v[2]; p.q[11] = N.y;
 		p.q[12] = w.x; p.q[13] = w.y; p.q[14] = w.z; p.q[15] = N.z;
+		return p;
+	}
+	static Box3 planar_box(int type, const float Q[3], const float u[3], const float v[3], const Xf& x) {
 		float f[9]; memcpy(f, Q, 12); memcpy(f + 3, u, 12); memcpy(f + 6, v, 12);
 		float pts[4][3]; quad_corners(f, pts);
 		const int cnt = type == PRIM_QUAD ? 4 : 3;
+		if (is_identity(x)) { Box3 b = box_of_points(pts, cnt); pad_to_minimum(b); return b; }
+		float wp[4][3];
+		for (int i = 0; i < cnt; ++i) x.point(pts[i], wp[i]);
+		Box3 b = box_of_points(wp, cnt); pad_to_minimum(b); pad_instance_box(b);
+		return b;
+	}
+	void emit_planar(int type, const float Q[3], const float u[3], const float v[3], int mat, int id, const Xf& x) {
+		const DevPrim p = planar_record(Q, u, v);
+		const Box3 b = planar_box(type, Q, u, v, x);
 		if (is_identity(x)) {
-			Box3 b = box_of_points(pts, cnt); pad_to_minimum(b);
 			emit(type, p, b, mat, id);
 		} else {
-			float wp[4][3];
-			for (int i = 0; i < cnt; ++i) x.point(pts[i], wp[i]);
-			Box3 b = box_of_points(wp, cnt); pad_to_minimum(b); pad_instance_box(b);
 			DevPrim t{}; put_xf(t.q, x);          // second slot: the transform
 			emit(type | PRIM_XF, p, b, mat, id, &t);
 		}
@@ -728,12 +741,31 @@ struct Flattener {
 		const float* mn = o.f; const float* mx = o.f + 3;
 		float dx[3] = {mx[0] - mn[0], 0, 0}, dy[3] = {0, mx[1] - mn[1], 0}, dz[3] = {0, 0, mx[2] - mn[2]};
 		float ndx[3] = {-dx[0], -dx[1], -dx[2]}, ndz[3] = {-dz[0], -dz[1], -dz[2]};   // full negation (signed zeros as in -dx)
-		float q0[3] = {mn[0], mn[1], mx[2]}; emit_planar(PRIM_QUAD, q0, dx, dy, o.mat, id, x);
-		float q1[3] = {mx[0], mn[1], mx[2]}; emit_planar(PRIM_QUAD, q1, ndz, dy, o.mat, id, x);
-		float q2[3] = {mx[0], mn[1], mn[2]}; emit_planar(PRIM_QUAD, q2, ndx, dy, o.mat, id, x);
-		float q3[3] = {mn[0], mn[1], mn[2]}; emit_planar(PRIM_QUAD, q3, dz, dy, o.mat, id, x);
-		float q4[3] = {mn[0], mx[1], mx[2]}; emit_planar(PRIM_QUAD, q4, dx, ndz, o.mat, id, x);
-		float q5[3] = {mn[0], mn[1], mn[2]}; emit_planar(PRIM_QUAD, q5, dx, dz, o.mat, id, x);
+		const float q[6][3] = {{mn[0], mn[1], mx[2]}, {mx[0], mn[1], mx[2]}, {mx[0], mn[1], mn[2]}, {mn[0], mn[1], mn[2]}, {mn[0], mx[1], mx[2]}, {mn[0], mn[1], mn[2]}};
+		const float* us[6] = {dx, ndz, ndx, dz, dx, dx};
+		const float* vs[6] = {dy, dy, dy, dy, ndz, dz};
+		if (box_as_quads) {
+			for (int f = 0; f < 6; ++f) emit_planar(PRIM_QUAD, q[f], us[f], vs[f], o.mat, id, x);
+			return;
+		}
+		// One BVH leaf: a (min, max) record the kernel uses to pick which faces the ray can hit, then the same six quad
+		// records as above; the kernel runs the ordinary quad test on the picked ones and reports the hit on that quad.
+		const bool inst = !is_identity(x);
+		Item it{}; it.first = (int)recs.size(); it.type = inst ? (PRIM_BOX | PRIM_XF) : PRIM_BOX; it.info.material = o.mat; it.info.object = id;
+		DevPrim t{}; if (inst) put_xf(t.q, x);
+		DevPrim bp{};
+		bp.q[0] = mn[0]; bp.q[1] = mn[1]; bp.q[2] = mn[2]; bp.q[3] = mx[0]; bp.q[4] = mx[1]; bp.q[5] = mx[2];
+		recs.push_back(bp); rec_type.push_back(it.type);
+		if (inst) { recs.push_back(t); rec_type.push_back(-1); }
+		Box3 b = empty_box();
+		for (int f = 0; f < 6; ++f) {
+			recs.push_back(planar_record(q[f], us[f], vs[f])); rec_type.push_back(inst ? (PRIM_QUAD | PRIM_XF) : PRIM_QUAD);
+			if (inst) { recs.push_back(t); rec_type.push_back(-1); }
+			grow(b, planar_box(PRIM_QUAD, q[f], us[f], vs[f], x));
+		}
+		it.nrec = (int)recs.size() - it.first;
+		items.push_back(it);
+		prim_boxes.push_back(b);
 	}
 	// Resolve a medium boundary: SPHERE or BOX under any chain of translate / rotate_y.
 	int emit_medium(const rtbs_object& med, int id, Xf x) {
@@ -815,8 +847,9 @@ int flatten(rtb_scene& s, FlatScene& out, const GpuBuildContext* gpu) {
 		t_lap = t1;
 	};
 	out = FlatScene();
-	Flattener fl{s, out, {}, {}};
-	fl.items.reserve(s.objects.size()); fl.prim_boxes.reserve(s.objects.size());
+	Flattener fl{s, out};
+	fl.items.reserve(s.objects.size()); fl.prim_boxes.reserve(s.objects.size()); fl.recs.reserve(s.objects.size()); fl.rec_type.reserve(s.objects.size());
+	{ const char* e = getenv("RTB_BOX_AS_QUADS"); fl.box_as_quads = e && e[0] == '1'; }
 	Xf ident;
 	int rc = fl.walk(s.root, ident, 0);
 	if (rc) return rc;
@@ -839,7 +872,7 @@ int flatten(rtb_scene& s, FlatScene& out, const GpuBuildContext* gpu) {
 		for (int m : media) {
 			const Flattener::Item& it = fl.items[m];
 			out.pre_list.push_back((int32_t)(((int)out.prims.size() << RTB_LEAF_TYPE_BITS) | it.type));
-			for (int k = 0; k < it.nrec; ++k) { out.prims.push_back(it.rec[k]); out.prim_info.push_back(it.info); out.prim_type.push_back(k == 0 ? it.type : -1); }
+			for (int k = 0; k < it.nrec; ++k) { out.prims.push_back(fl.recs[it.first + k]); out.prim_info.push_back(it.info); out.prim_type.push_back(fl.rec_type[it.first + k]); }
 		}
 		rest.reserve(fl.items.size()); rest_boxes.reserve(fl.items.size());
 		for (size_t i = 0; i < fl.items.size(); ++i) if (!is_pre[i]) { rest.push_back(fl.items[i]); rest_boxes.push_back(fl.prim_boxes[i]); }
@@ -903,7 +936,7 @@ int flatten(rtb_scene& s, FlatScene& out, const GpuBuildContext* gpu) {
 	parallel_for(order.size(), [&](size_t a, size_t b) {
 		for (size_t i = a; i < b; ++i) {
 			const Flattener::Item& it = fl.items[order[i]];
-			for (int k = 0; k < it.nrec; ++k) { out.prims[slot_of[i] + k] = it.rec[k]; out.prim_info[slot_of[i] + k] = it.info; out.prim_type[slot_of[i] + k] = k == 0 ? it.type : -1; }
+			for (int k = 0; k < it.nrec; ++k) { out.prims[slot_of[i] + k] = fl.recs[it.first + k]; out.prim_info[slot_of[i] + k] = it.info; out.prim_type[slot_of[i] + k] = fl.rec_type[it.first + k]; }
 		}
 	});
 	lap("layout");

@@ -15,6 +15,7 @@ namespace rtb {
 enum PrimType : int {
 	PRIM_SPHERE = 0, PRIM_MOVING_SPHERE = 1, PRIM_QUAD = 2, PRIM_TRIANGLE = 3,
 	PRIM_MEDIUM_SPHERE = 4, PRIM_MEDIUM_BOX = 5,
+	PRIM_BOX = 6,   // one BVH leaf for a book box(): (min, max) record followed by its six quad records (hits are reported on those)
 	PRIM_XF = 8
 };
 #define RTB_LEAF_TYPE_BITS 4

@@ -95,9 +95,11 @@ def test_flattener(rtb):
     assert stats["book2_bouncing"]["primitives"] == 488 and stats["book2_bouncing"]["inner_nodes"] == 487
     s = rtb.Scene.named("book2_bouncing"); s.set_world_bvh(rtb.WORLD_BVH_AS_BUILT)
     assert s.flatten_stats() == {"primitives": 488, "record_slots": 488, "inner_nodes": 487, "depth": 10}
-    assert stats["book2_cornell"]["primitives"] == 18 and stats["book2_cornell"]["record_slots"] == 30      # 12 instanced quads take 2 slots
+    # a box is ONE leaf: a (min, max) record + its six quad records, each followed by the transform when instanced
+    assert stats["book2_cornell"]["primitives"] == 6 + 2 and stats["book2_cornell"]["record_slots"] == 6 + 2 * 14
     assert stats["book2_cornell_smoke"]["primitives"] == 6                                                   # two media live in the pre-test list
-    assert stats["book2_final"]["primitives"] == 400 * 6 + 1 + 4 + 2 + 1000                                  # boxes, light, spheres, textured, cluster
+    assert stats["book2_final"]["primitives"] == 400 + 1 + 4 + 2 + 1000                                      # boxes, light, spheres, textured, cluster
+    assert stats["book2_final"]["record_slots"] == 400 * 7 + 1 + 4 + 2 + 1000 + 2                            # (+ the two media of the pre-test list)
     assert all(v["depth"] <= 30 for v in stats.values())
     s = rtb.Scene(); s.set_root(s.sphere((0, 0, 0), 1.0, s.lambertian(albedo=(1, 1, 1))))
     assert s.flatten_stats() == {"primitives": 1, "record_slots": 1, "inner_nodes": 0, "depth": 1}
