@@ -99,6 +99,11 @@ int rtb_add_triangle(rtb_scene* s, const float Q[3], const float u[3], const flo
 int rtb_add_box(rtb_scene* s, const float a[3], const float b[3], int mat);
 int rtb_add_list(rtb_scene* s, const int* children, int n);
 int rtb_add_bvh(rtb_scene* s, const int* children, int n, int builder);
+/* A triangle mesh in one call: `vertices` = n_vertices x (x, y, z), `indices` = n_triangles x 3 vertex indices.  Adds one
+ * triangle (Q = v0, u = v1 - v0, v = v2 - v0) per face that has an area and returns a BVH group over them - the same
+ * objects rtb_add_triangle + rtb_add_bvh would make (the reference has no mesh type; its GL demo loads OBJ files through
+ * tiny_obj, main/src/gl_engine/gl_mesh.cpp:124-218). */
+int rtb_add_mesh(rtb_scene* s, const float* vertices, int n_vertices, const int* indices, int n_triangles, int mat);
 int rtb_add_translate(rtb_scene* s, int child, const float offset[3]);
 int rtb_add_rotate_y(rtb_scene* s, int child, float degrees);
 int rtb_add_constant_medium(rtb_scene* s, int boundary, float density, int phase_mat);
@@ -118,6 +123,8 @@ enum rtb_world_bvh_mode { RTB_WORLD_BVH_QUALITY = 0, RTB_WORLD_BVH_AS_BUILT = 1,
 int rtb_scene_set_world_bvh(rtb_scene* s, int mode);
 
 int rtb_scene_num_objects(const rtb_scene* s);
+/* Children of a list / BVH / mesh group (1 for translate, rotate_y, constant_medium; 0 for primitives). */
+int rtb_scene_num_children(const rtb_scene* s, int object);
 /* World-space bounds of an object: out6 = {min.xyz, max.xyz} (getSphereBounds & co). */
 int rtb_object_bounds(const rtb_scene* s, int object, float out6[6]);
 

@@ -109,12 +109,14 @@ ABI = {
     "rtb_add_box": (C.c_int, [_P, _F3, _F3, C.c_int]),
     "rtb_add_list": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int]),
     "rtb_add_bvh": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int, C.c_int]),
+    "rtb_add_mesh": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int]),
     "rtb_add_translate": (C.c_int, [_P, C.c_int, _F3]),
     "rtb_add_rotate_y": (C.c_int, [_P, C.c_int, C.c_float]),
     "rtb_add_constant_medium": (C.c_int, [_P, C.c_int, C.c_float, C.c_int]),
     "rtb_scene_set_root": (C.c_int, [_P, C.c_int]),
     "rtb_scene_set_background": (C.c_int, [_P, C.c_int, _F3]),
     "rtb_scene_set_world_bvh": (C.c_int, [_P, C.c_int]),
+    "rtb_scene_num_children": (C.c_int, [_P, C.c_int]),
     "rtb_scene_num_objects": (C.c_int, [_P]),
     "rtb_object_bounds": (C.c_int, [_P, C.c_int, _F3]),
     "rtb_scene_serialize": (C.c_size_t, [_P, _P, C.c_size_t]),
@@ -290,6 +292,11 @@ class Scene:
     def bvh(self, children, builder=BVH_TOPDOWN_MEDIAN):
         arr = (C.c_int * len(children))(*children)
         return _check(lib().rtb_add_bvh(self.handle, arr, len(children), builder), "rtb_add_bvh")
+    def mesh(self, vertices, indices, mat):
+        """Triangle mesh from (n, 3) float32 vertices and (m, 3) int32 vertex indices: one BVH group of triangles."""
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3); i = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1, 3)
+        return _check(lib().rtb_add_mesh(self.handle, v.ctypes.data, len(v), i.ctypes.data, len(i), mat), "rtb_add_mesh")
+
     def translate(self, child, off): return _check(lib().rtb_add_translate(self.handle, child, _f3(off)), "rtb_add_translate")
     def rotate_y(self, child, deg): return _check(lib().rtb_add_rotate_y(self.handle, child, deg), "rtb_add_rotate_y")
     def constant_medium(self, boundary, density, phase): return _check(lib().rtb_add_constant_medium(self.handle, boundary, density, phase), "rtb_add_constant_medium")

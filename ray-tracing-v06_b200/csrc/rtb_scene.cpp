@@ -236,6 +236,25 @@ int rtb_add_bvh(rtb_scene* s, const int* ch, int n, int builder) {
 	if (n < 1) return fail(RTB_ERR_INVALID, "rtb_add_bvh: needs at least one child");
 	return add_group(s, RTB_OBJ_BVH, ch, n, builder);
 }
+int rtb_add_mesh(rtb_scene* s, const float* vertices, int n_vertices, const int* indices, int n_triangles, int mat) {
+	if (!s || !vertices || !indices || n_vertices < 3 || n_triangles < 1 || !mat_ok(s, mat)) return fail(RTB_ERR_INVALID, "rtb_add_mesh: bad argument");
+	for (int i = 0; i < 3 * n_triangles; ++i) if (indices[i] < 0 || indices[i] >= n_vertices) return fail(RTB_ERR_INVALID, "rtb_add_mesh: vertex index out of range");
+	std::vector<int> ids; ids.reserve(n_triangles);
+	s->objects.reserve(s->objects.size() + (size_t)n_triangles + 1);
+	for (int t = 0; t < n_triangles; ++t) {
+		const float* a = vertices + 3 * (size_t)indices[3 * t];
+		const float* b = vertices + 3 * (size_t)indices[3 * t + 1];
+		const float* c = vertices + 3 * (size_t)indices[3 * t + 2];
+		const float u[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, v[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+		// no area: nothing to hit, and the quad constants would be NaN.  (Plain products here, not the path's fma cross:
+		// fma(a, b, -(b * a)) is the rounding residue of the product, so cross(u, u) would not be exactly zero.)
+		const float nx = u[1] * v[2] - u[2] * v[1], ny = u[2] * v[0] - u[0] * v[2], nz = u[0] * v[1] - u[1] * v[0];
+		if (!(nx * nx + ny * ny + nz * nz > 0.0f)) continue;
+		ids.push_back(add_planar(s, RTB_OBJ_TRIANGLE, a, u, v, mat));
+	}
+	if (ids.empty()) return fail(RTB_ERR_INVALID, "rtb_add_mesh: no triangle has an area");
+	return add_group(s, RTB_OBJ_BVH, ids.data(), (int)ids.size(), RTB_BVH_TOPDOWN_MEDIAN);
+}
 int rtb_add_translate(rtb_scene* s, int child, const float off[3]) {
 	if (!s || !off || !obj_ok(s, child)) return fail(RTB_ERR_INVALID, "rtb_add_translate: bad argument");
 	rtbs_object o = blank_object(RTB_OBJ_TRANSLATE, -1);
@@ -274,6 +293,10 @@ int rtb_scene_set_background(rtb_scene* s, int mode, const float rgb[3]) {
 	return RTB_OK;
 }
 int rtb_scene_num_objects(const rtb_scene* s) { return s ? (int)s->objects.size() : RTB_ERR_INVALID; }
+int rtb_scene_num_children(const rtb_scene* s, int object) {
+	if (!s || !obj_ok(s, object)) return fail(RTB_ERR_INVALID, "rtb_scene_num_children: bad argument");
+	return s->objects[object].child_count;
+}
 
 }  // extern "C"
 

@@ -64,20 +64,14 @@ public:
 	template <typename MatType> requires GeoAcceptableMat<Triangle, MatType>
 	static MeshHandle MakeMesh(const Mesh& mesh, MatType* mat) {
 		MeshHandle h{};
-		std::vector<int> ids;
-		for (size_t t = 0; t + 2 < mesh.indices.size(); t += 3) {
-			const glm::vec3 a = mesh.vertices[mesh.indices[t]], b = mesh.vertices[mesh.indices[t + 1]], c = mesh.vertices[mesh.indices[t + 2]];
-			const glm::vec3 u = b - a, v = c - a;
-			const glm::vec3 n = glm::cross(u, v);
-			if (!(glm::dot(n, n) > 0.0f)) continue;                 // degenerate face: no area, nothing to hit
-			ids.push_back(rtb_host::check(rtb_add_triangle(rtb_host::scene(), &a.x, &u.x, &v.x, mat->rtb_material), "MakeMesh"));
-		}
-		if (ids.empty()) throw std::runtime_error("MeshHandle::MakeMesh: mesh has no non-degenerate triangles");
-		int group = rtb_host::check(rtb_add_bvh(rtb_host::scene(), ids.data(), (int)ids.size(), RTB_BVH_TOPDOWN_MEDIAN), "MakeMesh");
+		static_assert(sizeof(glm::vec3) == 3 * sizeof(float), "vertices are handed over as packed floats");
+		const int group = rtb_host::check(rtb_add_mesh(rtb_host::scene(), &mesh.vertices[0].x, (int)mesh.vertices.size(), mesh.indices.data(),
+		                                               (int)(mesh.indices.size() / 3), mat->rtb_material), "MakeMesh");
+		const int faces = rtb_host::check(rtb_scene_num_children(rtb_host::scene(), group), "MakeMesh");
 		float bb[6]; rtb_host::check(rtb_object_bounds(rtb_host::scene(), group, bb), "rtb_object_bounds");
 		h.bounds = aabb(glm::vec3(bb[0], bb[1], bb[2]), glm::vec3(bb[3], bb[4], bb[5]));
 		h.hittable_ptr = new GeoHittable(group);
-		h.triangle_count = (int)ids.size();
+		h.triangle_count = faces;
 		return h;
 	}
 	const Hittable* getHittablePtr() const { return hittable_ptr; }

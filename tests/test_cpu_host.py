@@ -214,3 +214,21 @@ def test_gpu_lbvh_mode_needs_a_renderer(rtb):
         s.set_world_bvh(7)
     s.set_world_bvh(rtb.WORLD_BVH_QUALITY)
     assert s.flatten_stats()["primitives"] == 488
+
+
+def test_add_mesh_equals_triangles_under_a_bvh(rtb):
+    """rtb_add_mesh(vertices, indices) makes exactly the objects rtb_add_triangle + rtb_add_bvh make (faces without area dropped)."""
+    rng = np.random.default_rng(3)
+    v = rng.random((50, 3), dtype=np.float32) * 4 - 2
+    idx = rng.integers(0, 50, (120, 3)).astype(np.int32)
+    idx[7] = [3, 3, 9]; idx[20] = [5, 5, 5]                     # two faces without area
+    a = rtb.Scene(); ma = a.lambertian(albedo=(0.5, 0.5, 0.5)); ga = a.mesh(v, idx, ma); a.set_root(ga)
+    b = rtb.Scene(); mb = b.lambertian(albedo=(0.5, 0.5, 0.5))
+    ids = [b.triangle(tuple(v[i]), tuple(v[j] - v[i]), tuple(v[k] - v[i]), mb) for i, j, k in idx if len({i, j, k}) == 3]
+    b.set_root(b.bvh(ids))
+    assert a.serialize() == b.serialize()
+    assert a.flatten_stats() == b.flatten_stats() and a.flatten_stats()["primitives"] == len(ids)
+    with pytest.raises(rtb.RtbError):
+        a.mesh(v, np.array([[0, 1, 50]], dtype=np.int32), ma)   # index out of range
+    with pytest.raises(rtb.RtbError):
+        a.mesh(v, np.array([[4, 4, 4]], dtype=np.int32), ma)    # nothing with an area

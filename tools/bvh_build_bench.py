@@ -20,13 +20,11 @@ def height_field(n):
     xs = np.linspace(-1, 1, n + 1, dtype=np.float32)
     X, Z = np.meshgrid(xs, xs, indexing="ij")
     Y = (0.08 * np.sin(9 * X) * np.cos(7 * Z) + 0.03 * np.sin(31 * X + 17 * Z)).astype(np.float32)
-    P = np.stack([X, Y, Z], axis=-1)
-    ids = []
-    tri = s.triangle
-    for i in range(n):
-        for j in range(n):
-            a, b, c, d = P[i, j], P[i + 1, j], P[i, j + 1], P[i + 1, j + 1]
-            ids.append(tri(tuple(a), tuple(b - a), tuple(c - a), m)); ids.append(tri(tuple(d), tuple(b - d), tuple(c - d), m))
+    P = np.stack([X, Y, Z], axis=-1).reshape(-1, 3)
+    i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    v00 = (i * (n + 1) + j).ravel(); v10 = v00 + (n + 1); v01 = v00 + 1; v11 = v10 + 1
+    tris = np.concatenate([np.stack([v00, v10, v01], axis=1), np.stack([v11, v10, v01], axis=1)]).astype(np.int32)
+    ids = [s.mesh(P, tris, m)]
     ids.append(s.sphere((0.0, 0.35, 0.0), 0.25, g))
     s.set_root(s.list(ids))
     cam = rtb.make_camera("pinhole", (1.6, 1.1, 1.9), (0, 0, 0), (0, 1, 0), 40.0, 1.0)
