@@ -257,8 +257,8 @@ def main():
                 "peak_source": peak_src, "algorithmic_bytes_per_ray": ALG_BYTES_PER_RAY_TRAVERSE,
                 "avg_launch_ms": prof.traverse_ms / max(1, prof.traverse_launches), "launches": int(prof.traverse_launches),
                 "note": "traversal is instruction-issue bound with SIMT divergence (scene is L1/L2 resident); HBM carries only the wavefront queues",
-                "issue": {"source": "profiles/r1_traverse_ncu.txt (ncu --set full, static)", "issue_slots_busy_pct": 69, "alu_pipe_busy_pct": 50,
-                          "fma_pipe_busy_pct": 28, "active_lanes_per_instruction": {"primary_rays": 24.4, "bounce_1": 12.0, "bounce_2": 10.6}}}
+                "issue": {"source": "profiles/r1_traverse_ncu.txt (ncu --set full, static)", "issue_slots_busy_pct": 67, "alu_pipe_busy_pct": 56,
+                          "fma_pipe_busy_pct": 30, "l1_data_pipe_busy_pct": 57, "active_lanes_per_instruction": {"primary_rays": 25.0, "bounce_1": 12.4, "bounce_2": 10.8}}}
         step_bytes = ALG_BYTES_PER_RAY_STEP * rays + ALG_BYTES_PER_PATH_STEP * paths
         split = {"traverse_ms": prof.traverse_ms, "shade_ms": prof.shade_ms, "generate_ms": prof.generate_ms, "accumulate_ms": prof.accumulate_ms, "tail_ms": prof.tail_ms,
                  "traverse_share": prof.traverse_ms / total_ms if total_ms else None,
