@@ -212,18 +212,24 @@ __device__ __forceinline__ float box_hit(v3 o, v3 d, float idx, float idy, float
 // only when some medium's boundary interval survives the geometric rejections, and shared by up to
 // four media.
 struct MediumRng {
-	uint32_t seed, pixel, sample, bounce;
+	uint32_t seed, path, bounce;
+	uint32_t npix, pixel0, sample0;   // batch layout (warp-uniform): the path's pixel and sample are only worked out
+	                                  // (an integer division) when a block of uniforms is actually drawn
 	uint32_t block;    // cached block index, 0xFFFFFFFF = none
 	rt::f4 u;
 	__device__ __forceinline__ float get(uint32_t m) {
 		const uint32_t b = m >> 2;
-		if (b != block) { u = rt::rng4(seed, pixel, sample, bounce, rt::STREAM_MEDIUM0 + b); block = b; }
+		if (b != block) {
+			const uint32_t sl = path / npix, pl = path - sl * npix;      // path_pixel_sample
+			u = rt::rng4(seed, pixel0 + pl, sample0 + sl, bounce, rt::STREAM_MEDIUM0 + b); block = b;
+		}
 		const uint32_t c = m & 3u;
 		return c == 0 ? u.x : (c == 1 ? u.y : (c == 2 ? u.z : u.w));
 	}
 };
-__device__ __forceinline__ MediumRng make_medium_rng(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce) {
-	MediumRng r; r.seed = seed; r.pixel = pixel; r.sample = sample; r.bounce = bounce; r.block = 0xFFFFFFFFu;
+__device__ __forceinline__ MediumRng make_medium_rng(const BatchParams& bp, uint32_t batch, uint32_t path, uint32_t bounce) {
+	MediumRng r; r.seed = bp.seed; r.path = path; r.bounce = bounce; r.block = 0xFFFFFFFFu;
+	r.npix = bp.npix; r.pixel0 = bp.row_begin * bp.width; r.sample0 = bp.sample_begin + batch * bp.samples_per_batch;
 	r.u.x = r.u.y = r.u.z = r.u.w = 0.0f; return r;
 }
 
@@ -480,8 +486,7 @@ traverse_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
 		const uint32_t i = base + lane;
 		if (i < n) {
 			const float4 fo = ro[i], fd = rd[i];
-			MediumRng mr = make_medium_rng(bp.seed, 0, 0, bounce);
-			if (MEDIA) path_pixel_sample(bp, batch, __float_as_uint(fd.w), mr.pixel, mr.sample);
+			MediumRng mr = make_medium_rng(bp, batch, __float_as_uint(fd.w), bounce);
 			float t; int code;
 			trace_ray<MEDIA>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code);
 			wv.hit[i] = make_int2(__float_as_int(t), code);
@@ -838,8 +843,7 @@ tail_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce0, uint32_
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
 		float4 fo = ro[i], fd = rd[i];
 		v3 thr = xyz(rt_[i]);
-		MediumRng mr = make_medium_rng(bp.seed, 0, 0, bounce0);
-		if (MEDIA) path_pixel_sample(bp, batch, __float_as_uint(fd.w), mr.pixel, mr.sample);
+		MediumRng mr = make_medium_rng(bp, batch, __float_as_uint(fd.w), bounce0);
 		for (uint32_t b = bounce0; b < bp.max_depth; ++b) {
 			if (b > bounce0) ++extra;
 			mr.bounce = b; mr.block = 0xFFFFFFFFu;
@@ -922,7 +926,7 @@ trace_rays_kernel(SceneView sv, const float4* __restrict__ ro, const float4* __r
 		uint32_t i = base + lane;
 		if (i < n) {
 			float4 fo = ro[i], fd = rd[i];
-			MediumRng mr = make_medium_rng(0, 0, 0, 0);
+			MediumRng mr = make_medium_rng(BatchParams{}, 0, 0, 0);
 			float t; int code;
 			int st[2];
 			trace_ray<0, true>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code, st);
