@@ -441,6 +441,7 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 			else if (hr) cur = n3.y;
 			else if (sp > 0) { --sp; cur = stack[sp * TRAVERSE_THREADS]; }
 			else cur = TRAV_END;
+
 #if !TRAV_WHILE_WHILE
 			break;   // if-if flavour: at most one inner node per trip
 #endif
