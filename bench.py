@@ -316,9 +316,13 @@ def main():
             "cpu_baseline": cpu, "psnr_vs_oracle_db": psnr_db,
             "reference_gpu": refgpu,
         }
-        print(json.dumps(line), file=_JSON_OUT, flush=True)
+    else:
+        line = None
     if world > 1:
         dist.destroy_process_group()
+    if line is not None:                       # last thing this process writes anywhere
+        sys.stderr.flush()
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 if __name__ == "__main__":
