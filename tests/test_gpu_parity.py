@@ -191,6 +191,64 @@ def test_sample_ranges_and_batches_compose(rtb, renderer):
     assert np.array_equal(rows, whole), "row partition changes the image"
 
 
+def test_full_size_properties(rtb, renderer):
+    """BASELINE's headline configuration (Book 2 final scene, 800x800, depth 40) is too large for the oracle, so it is
+    checked through properties that do not depend on size: sample ranges and row ranges compose, the image does not
+    depend on which world BVH is walked or on the batch size, the ray count is the same every time, and the output
+    is a finite image in [0, 1] with alpha 1."""
+    scene = rtb.Scene.named("book2_final"); cam = scene.info.camera
+    W, H, D, SPP = scene.info.width, scene.info.height, scene.info.max_depth, 6
+    assert (W, H, D) == (800, 800, 40)
+    renderer.set_scene(scene); renderer.set_camera(cam)
+    renderer.reset_counters(); renderer.render(W, H, 0, SPP, D, seed=1984); whole = renderer.download_accum(); c0 = renderer.counters()
+    assert c0.paths == W * H * SPP and c0.rays > 4 * c0.paths
+    assert np.isfinite(whole).all() and np.array_equal(whole[..., 3], np.full((H, W), SPP, dtype=np.float32)) and (whole[..., :3] >= 0).all()
+    out = renderer.download()
+    assert np.isfinite(out).all() and out[..., :3].min() >= 0.0 and out[..., :3].max() <= 1.0 and (out[..., 3] == 1.0).all()
+    # sample ranges add up (float addition order differs: allclose), rows partition exactly
+    renderer.render(W, H, 0, 2, D, seed=1984); renderer.render(W, H, 2, SPP, D, seed=1984, clear=False)
+    np.testing.assert_allclose(renderer.download_accum(), whole, rtol=1e-5, atol=1e-5)
+    renderer.reset_counters()
+    renderer.render(W, H, 0, SPP, D, seed=1984, rows=(0, 333)); renderer.render(W, H, 0, SPP, D, seed=1984, rows=(333, H), clear=False)
+    assert np.array_equal(renderer.download_accum(), whole) and renderer.counters().rays == c0.rays
+    # batch size (1.28 M-path batches instead of one 3.84 M-path batch): same paths, same sums per pixel
+    renderer.reset_counters(); renderer.render(W, H, 0, SPP, D, seed=1984, samples_per_batch=2)
+    np.testing.assert_allclose(renderer.download_accum(), whole, rtol=1e-5, atol=1e-5)     # (per-pixel sums associate differently)
+    assert renderer.counters().rays == c0.rays
+    # the tree does not matter: the GPU-built linear BVH gives the same image, path for path
+    scene.set_world_bvh(rtb.WORLD_BVH_GPU_LBVH); renderer.set_scene(scene)
+    assert renderer.scene_stats()["builder"] == "gpu_lbvh"
+    renderer.reset_counters(); renderer.render(W, H, 0, SPP, D, seed=1984); lb = renderer.download_accum()
+    scene.set_world_bvh(rtb.WORLD_BVH_QUALITY)
+    differing = (np.abs(lb[..., :3] - whole[..., :3]).max(axis=2) > 1e-4 * np.maximum(whole[..., :3].max(axis=2), 1.0)).mean()
+    assert differing < 1e-4 and abs(int(renderer.counters().rays) - int(c0.rays)) <= 1e-5 * c0.rays
+    # another seed is another image
+    renderer.set_scene(scene); renderer.render(W, H, 0, SPP, D, seed=7)
+    assert not np.array_equal(renderer.download_accum(), whole)
+
+
+def test_furnace_energy_is_conserved(rtb, renderer):
+    """White Lambertian boxes, spheres and an instanced box under a constant white background: every path carries
+    throughput exactly 1 until it escapes (radiance 1) or runs out of depth (radiance 0), so every accumulated sample is 0
+    or 1 exactly, whatever the geometry does — at the headline image size."""
+    s = rtb.Scene(); white = s.lambertian(albedo=(1.0, 1.0, 1.0))
+    rng = np.random.default_rng(5)
+    objs = [s.box((-30.0, -1.0, -30.0), (30.0, 0.0, 30.0), white)]
+    objs += [s.box((float(x), 0.0, float(z)), (float(x) + 1.5, float(rng.uniform(0.5, 3.0)), float(z) + 1.5), white) for x in range(-8, 8, 3) for z in range(-8, 8, 3)]
+    objs += [s.sphere((float(rng.uniform(-8, 8)), float(rng.uniform(0.5, 4)), float(rng.uniform(-8, 8))), float(rng.uniform(0.3, 1.0)), white) for _ in range(40)]
+    objs.append(s.translate(s.rotate_y(s.box((0.0, 0.0, 0.0), (2.0, 5.0, 2.0), white), 25.0), (3.0, 0.0, -2.0)))
+    s.set_root(s.list(objs)); s.set_background(rtb.BG_CONSTANT, (1.0, 1.0, 1.0))
+    cam = rtb.make_camera("pinhole", (14, 9, 16), (0, 1, 0), (0, 1, 0), 40.0, 1.0)
+    renderer.set_scene(s); renderer.set_camera(cam)
+    W = H = 800; SPP = 5
+    renderer.render(W, H, 0, SPP, 40, seed=3); acc = renderer.download_accum()
+    assert np.array_equal(acc[..., 3], np.full((H, W), SPP, dtype=np.float32))
+    rgb = acc[..., :3]
+    assert np.array_equal(rgb, np.round(rgb)) and rgb.min() >= 0 and rgb.max() <= SPP          # whole numbers of escaped paths
+    assert np.array_equal(rgb[..., 0], rgb[..., 1]) and np.array_equal(rgb[..., 0], rgb[..., 2])
+    assert 0.9 < rgb.mean() / SPP <= 1.0                                                        # nearly everything escapes within 40 bounces
+
+
 def test_download_matches_reference_tonemap(rtb, renderer):
     scene = rtb.Scene.named("book2_checker")
     renderer.set_scene(scene); renderer.set_camera(scene.info.camera)
