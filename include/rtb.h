@@ -155,6 +155,9 @@ int rtb_scene_world_bvh(const rtb_scene* s, rtb_bvh_node* nodes_out, int cap, in
  * reports its sizes; also fills the world BVH returned by rtb_scene_world_bvh.  out4 = {primitives
  * (BVH leaves), 64-byte record slots, inner nodes of the wide layout, tree depth}. */
 int rtb_scene_flatten_stats(rtb_scene* s, int32_t out4[4]);
+/* Host-only: FNV-1a hash of what the flattener would upload for traversal and shading (wide nodes, primitive records,
+ * per-slot material / object ids, pre-test list).  Two scenes, builds or settings that hash equal render identically. */
+int rtb_scene_flatten_hash(rtb_scene* s, uint64_t* hash_out);
 
 /* What rtb_renderer_set_scene last built (declared below with the renderer): sizes as in rtb_scene_flatten_stats,
  * the builder that produced the tree the kernels walk (an rtb_world_bvh_mode value, or RTB_BUILDER_MEDIAN_FALLBACK

@@ -122,6 +122,7 @@ ABI = {
     "rtb_scene_serialize": (C.c_size_t, [_P, _P, C.c_size_t]),
     "rtb_bvh_build": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_int)]),
     "rtb_scene_world_bvh": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int)]),
+    "rtb_scene_flatten_hash": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "rtb_scene_flatten_stats": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "rtb_camera_pinhole": (C.c_int, [C.POINTER(Camera), _F3, _F3, _F3, C.c_float, C.c_float]),
     "rtb_camera_defocus": (C.c_int, [C.POINTER(Camera), _F3, _F3, _F3, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
@@ -320,6 +321,11 @@ class Scene:
         out = (C.c_int32 * 4)()
         _check(lib().rtb_scene_flatten_stats(self.handle, out), "rtb_scene_flatten_stats")
         return {"primitives": out[0], "record_slots": out[1], "inner_nodes": out[2], "depth": out[3]}
+
+    def flatten_hash(self) -> int:
+        h = C.c_uint64(0)
+        _check(lib().rtb_scene_flatten_hash(self.handle, C.byref(h)), "rtb_scene_flatten_hash")
+        return int(h.value)
 
     def world_bvh(self):
         root = C.c_int(-1)

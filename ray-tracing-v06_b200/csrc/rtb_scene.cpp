@@ -538,7 +538,9 @@ int build_bvh_world_sah(const std::vector<Box3>& boxes, std::vector<rtb_bvh_node
 		return slot;
 	};
 	const int NB = 32, MAX_DEPTH = 26, PARALLEL_MIN = 16384;
-	const int max_fork_depth = n >= 2 * PARALLEL_MIN ? std::min(6, (int)std::ceil(std::log2(std::max(2u, std::thread::hardware_concurrency())))) + 1 : 0;
+	const char* serial_env = getenv("RTB_FLATTEN_SERIAL");   // =1: build on the calling thread only (the result is the same)
+	const bool serial = serial_env && serial_env[0] == '1';
+	const int max_fork_depth = serial ? 0 : n >= 2 * PARALLEL_MIN ? std::min(6, (int)std::ceil(std::log2(std::max(2u, std::thread::hardware_concurrency())))) + 1 : 0;
 	std::function<int(int, int, int, int)> rec = [&](int start, int end, int depth, int base) -> int {
 		const int slot = base + 2 * (end - start) - 2;      // this subtree's root: last of its 2 (end - start) - 1 slots
 		Box3 bounds = empty_box();
@@ -844,9 +846,10 @@ struct Flattener {
 		case RTB_OBJ_QUAD: emit_planar(PRIM_QUAD, o.f, o.f + 3, o.f + 6, o.mat, id, x); return RTB_OK;
 		case RTB_OBJ_TRIANGLE: emit_planar(PRIM_TRIANGLE, o.f, o.f + 3, o.f + 6, o.mat, id, x); return RTB_OK;
 		case RTB_OBJ_BOX: emit_box(o, id, x); return RTB_OK;
-		case RTB_OBJ_LIST: case RTB_OBJ_BVH:
+		case RTB_OBJ_LIST: case RTB_OBJ_BVH: {
 			for (int k = 0; k < o.child_count; ++k) { int rc = walk(s.children[o.child_begin + k], x, depth + 1); if (rc) return rc; }
 			return RTB_OK;
+		}
 		case RTB_OBJ_TRANSLATE: return walk(s.children[o.child_begin], compose_translate(x, o.f), depth + 1);
 		case RTB_OBJ_ROTATE_Y: return walk(s.children[o.child_begin], compose_rotate(x, o.f[1], o.f[2]), depth + 1);
 		case RTB_OBJ_CONSTANT_MEDIUM: return emit_medium(o, id, x);
@@ -1048,6 +1051,23 @@ extern "C" int rtb_scene_flatten_stats(rtb_scene* s, int32_t out4[4]) {
 	if (rc) return rc;
 	out4[0] = (int32_t)((s->world_nodes.size() + 1) / 2); out4[1] = (int32_t)fs.prims.size();
 	out4[2] = (int32_t)fs.nodes.size(); out4[3] = fs.max_depth_nodes;
+	return RTB_OK;
+}
+
+extern "C" int rtb_scene_flatten_hash(rtb_scene* s, uint64_t* hash_out) {
+	if (!s || !hash_out) return rtb::fail(RTB_ERR_INVALID, "rtb_scene_flatten_hash: null argument");
+	rtb::FlatScene fs;
+	int rc = rtb::flatten(*s, fs);
+	if (rc) return rc;
+	uint64_t h = 1469598103934665603ull;
+	auto mix = [&h](const void* p, size_t n) { const uint8_t* b = static_cast<const uint8_t*>(p); for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; } };
+	if (!fs.nodes.empty()) mix(fs.nodes.data(), fs.nodes.size() * sizeof(rtb::DevNode));
+	if (!fs.prims.empty()) mix(fs.prims.data(), fs.prims.size() * sizeof(rtb::DevPrim));
+	if (!fs.prim_info.empty()) mix(fs.prim_info.data(), fs.prim_info.size() * sizeof(rtb::DevPrimInfo));
+	if (!fs.prim_type.empty()) mix(fs.prim_type.data(), fs.prim_type.size() * sizeof(fs.prim_type[0]));
+	if (!fs.pre_list.empty()) mix(fs.pre_list.data(), fs.pre_list.size() * sizeof(fs.pre_list[0]));
+	mix(&fs.root_ref, sizeof fs.root_ref);
+	*hash_out = h;
 	return RTB_OK;
 }
 

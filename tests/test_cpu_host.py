@@ -232,3 +232,23 @@ def test_add_mesh_equals_triangles_under_a_bvh(rtb):
         a.mesh(v, np.array([[0, 1, 50]], dtype=np.int32), ma)   # index out of range
     with pytest.raises(rtb.RtbError):
         a.mesh(v, np.array([[4, 4, 4]], dtype=np.int32), ma)    # nothing with an area
+
+
+def test_flatten_is_deterministic_and_thread_count_independent(rtb, monkeypatch):
+    """What the flattener uploads (rtb_scene_flatten_hash) does not depend on how the work was spread over host threads:
+    large BVH subtrees are built by concurrent tasks and give the arrays of the serial build (RTB_FLATTEN_SERIAL=1)."""
+    import sys
+    sys.path.insert(0, str(ROOT / "tools"))
+    from bvh_build_bench import height_field
+    s, _ = height_field(200)                                   # 80,001 primitives: above the threshold for concurrent subtrees
+    h = s.flatten_hash()
+    assert h == s.flatten_hash()
+    monkeypatch.setenv("RTB_FLATTEN_SERIAL", "1")
+    assert s.flatten_hash() == h
+    monkeypatch.delenv("RTB_FLATTEN_SERIAL")
+    t = rtb.Scene.named("book2_final")
+    a = t.flatten_hash()
+    monkeypatch.setenv("RTB_BOX_AS_QUADS", "1")
+    assert t.flatten_hash() != a                               # (a different layout does hash differently)
+    monkeypatch.delenv("RTB_BOX_AS_QUADS")
+    assert t.flatten_hash() == a
