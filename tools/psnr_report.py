@@ -22,7 +22,7 @@ ONLY = sys.argv[2].split(",") if len(sys.argv) > 2 else None
 CASES = [  # name, W, H, depth, has reference streams
     ("book1_final", 240, 135, 50, True), ("book2_bouncing", 200, 112, 50, True), ("book2_checker", 200, 112, 50, False),
     ("book2_earth", 200, 112, 50, False), ("book2_perlin", 200, 112, 50, False), ("book2_cornell_smoke", 120, 120, 50, False),
-    ("book2_final", 160, 160, 40, False),
+    ("book2_final", 160, 160, 40, False), ("mesh_icospheres", 200, 112, 50, False),
 ]
 
 
