@@ -135,6 +135,19 @@ def run_reference_arm(args, rank, world):
 _JSON_OUT = sys.stdout
 
 
+def camera_rays_for(pkg, cam, width, height):
+    """Primary rays through pixel centres (Renderer.cu:192) as rtb_ray records, for the traversal-statistics hook."""
+    import numpy as np
+    xs = (np.arange(width, dtype=np.float32) + np.float32(0.5)) * (np.float32(1) / np.float32(width)) * np.float32(2) - np.float32(1)
+    ys = (np.arange(height, dtype=np.float32) + np.float32(0.5)) * (np.float32(1) / np.float32(height)) * np.float32(2) - np.float32(1)
+    U, V = np.meshgrid(xs, ys)
+    o = np.array(cam.o[:], dtype=np.float32); cu = np.array(cam.u[:], dtype=np.float32); cv = np.array(cam.v[:], dtype=np.float32); cw = np.array(cam.w[:], dtype=np.float32)
+    d = cw[None, None, :] + cu[None, None, :] * U[..., None] + cv[None, None, :] * V[..., None]
+    rays = np.zeros(width * height, dtype=pkg.RAY_DTYPE)
+    rays["o"] = o; rays["d"] = d.reshape(-1, 3).astype(np.float32); rays["time"] = 0.0
+    return rays
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -259,6 +272,28 @@ def main():
                 "note": "traversal is instruction-issue bound with SIMT divergence (scene is L1/L2 resident); HBM carries only the wavefront queues",
                 "issue": {"source": "profiles/r1_traverse_ncu.txt (ncu --set full, static)", "issue_slots_busy_pct": 67, "alu_pipe_busy_pct": 56,
                           "fma_pipe_busy_pct": 30, "l1_data_pipe_busy_pct": 57, "active_lanes_per_instruction": {"primary_rays": 25.0, "bounce_1": 12.4, "bounce_2": 10.8}}}
+        # FP32 work in SURVEY 8(d)'s accounting: 24 flop per box test, 30 per primitive test, 150 per shaded segment, with
+        # the box / primitive tests per ray counted live through the rtb_trace_rays hook on this scene's primary rays and
+        # one generation of diffuse secondary rays (the mix of a depth-40 path is dominated by the latter).
+        try:
+            cam_rays = camera_rays_for(pkg, info.camera, 200, 200)
+            h1 = r.trace_rays(cam_rays); hit1 = h1["object"] >= 0
+            rng = np.random.default_rng(0)
+            v = rng.normal(size=(int(hit1.sum()), 3)).astype(np.float32); v /= np.linalg.norm(v, axis=1, keepdims=True)
+            sec = np.zeros(int(hit1.sum()), dtype=pkg.RAY_DTYPE); dsec = h1["n"][hit1] + v
+            sec["o"] = h1["p"][hit1] + dsec * np.float32(0.001); sec["d"] = dsec; sec["time"] = 0.5
+            h2 = r.trace_rays(sec)
+            w_sec = 1.0 - paths / rays                                   # share of ray segments that are not camera rays
+            boxes = 2.0 * ((1 - w_sec) * float(h1["nodes_visited"].mean()) + w_sec * float(h2["nodes_visited"].mean()))
+            prims = (1 - w_sec) * float(h1["prims_tested"].mean()) + w_sec * float(h2["prims_tested"].mean())
+            flop_per_ray = 24.0 * boxes + 30.0 * prims + 150.0
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+            roof["fp32"] = {"achieved_tflops": flop_per_ray * (rays / world) / (ms * 1e-3) / 1e12, "peak_tflops": fp32_peak, "peak_note": f"148 SMs x 128 lanes x 2 x {sm_mhz:.0f} MHz (non-tensor FP32)",
+                            "frac": flop_per_ray * (rays / world) / (ms * 1e-3) / 1e12 / fp32_peak, "box_tests_per_ray": boxes, "prim_tests_per_ray": prims, "flop_per_ray": flop_per_ray,
+                            "model": "24 flop / box test + 30 / primitive test + 150 / shaded segment (SURVEY 8d); tests per ray measured through rtb_trace_rays"}
+        except Exception as e:   # the counters are diagnostics: never fail the bench line over them
+            roof["fp32"] = {"error": str(e)}
         step_bytes = ALG_BYTES_PER_RAY_STEP * rays + ALG_BYTES_PER_PATH_STEP * paths
         split = {"traverse_ms": prof.traverse_ms, "shade_ms": prof.shade_ms, "generate_ms": prof.generate_ms, "accumulate_ms": prof.accumulate_ms, "tail_ms": prof.tail_ms,
                  "traverse_share": prof.traverse_ms / total_ms if total_ms else None,
