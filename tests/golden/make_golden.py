@@ -20,6 +20,9 @@ Fixtures:
   ref_megakernel_200x112_4spp_d50.bin      raw float4 framebuffer of the reference's render_kernel (first Render call)
   ref_megakernel_400x225_100spp_d50_f16.npy  same at config 2's size, stored as float16 RGB
   ref_bvh_book2_bouncing.bin               node array + primitive order of the reference's BuildBVH_TopDown
+  oracle_images_32x18.npz                  (`python tests/golden/make_golden.py oracle`) the ORACLE's own Philox renders of every
+                                           registered scene at 32x18, 2 spp, depth 8 - not a reference fixture: a tripwire that
+                                           the oracle (the checker of every GPU test) has not drifted
 """
 import importlib
 import shutil
@@ -33,6 +36,18 @@ import numpy as np
 ROOT = Path(__file__).resolve().parents[2]
 GOLD = ROOT / "tests" / "golden"
 sys.path.insert(0, str(ROOT))
+
+
+def oracle_images():
+    rtb = importlib.import_module("ray-tracing-v06_b200")
+    sys.path.insert(0, str(ROOT / "oracle")); orc = importlib.import_module("pyoracle")
+    out = {}
+    for name in rtb.scene_names():
+        s = rtb.Scene.named(name)
+        acc, _, rays = orc.OracleScene(s.serialize()).render(s.info.camera, 32, 18, 0, 2, 8, seed=1984)
+        out[name] = acc.astype(np.float32); out[name + "__rays"] = np.array([rays], dtype=np.int64)
+    np.savez_compressed(GOLD / "oracle_images_32x18.npz", **out)
+    print("wrote", GOLD / "oracle_images_32x18.npz", len(out) // 2, "scenes")
 
 
 def bvh():
@@ -56,4 +71,4 @@ def collect():
 
 
 if __name__ == "__main__":
-    {"bvh": bvh, "collect": collect}[sys.argv[1]]()
+    {"bvh": bvh, "collect": collect, "oracle": oracle_images}[sys.argv[1]]()

@@ -211,3 +211,17 @@ def test_edge_cases(rtb, orc):
     assert h["t"][0] == 10.0 and h["t"][3] == 10.0               # from the centre of the lower sphere: near root < 0, far root taken
     with pytest.raises(RuntimeError):
         orc.OracleScene(b"not a scene")
+
+
+def test_oracle_has_not_drifted(rtb, orc):
+    """The oracle is the checker of every GPU test, so it gets a tripwire of its own: its Philox renders of every
+    registered scene (32x18, 2 spp, depth 8) against the committed copies (tests/golden/make_golden.py oracle)."""
+    from conftest import ROOT
+    gold = np.load(ROOT / "tests" / "golden" / "oracle_images_32x18.npz")
+    names = rtb.scene_names()
+    assert sorted(k for k in gold.files if not k.endswith("__rays")) == sorted(names)
+    for name in names:
+        s = rtb.Scene.named(name)
+        acc, _, rays = orc.OracleScene(s.serialize()).render(s.info.camera, 32, 18, 0, 2, 8, seed=1984)
+        assert rays == int(gold[name + "__rays"][0]), name
+        np.testing.assert_allclose(acc, gold[name], rtol=1e-6, atol=1e-6, err_msg=name)
