@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--cpu-spp", type=int, default=128, help="samples per pixel of the cpu_baseline sample (rank 0, N=1)")
     ap.add_argument("--ref-spp", type=int, default=16, help="samples per pixel per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference megakernel run beside ours (A/B runs)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -319,7 +320,7 @@ def main():
     # ---- the reference's own GPU megakernel on the one config it can express (cfg 2), beside ours
     refgpu = None
     ref_bin = ROOT / "oracle" / "_ref" / "ref_render"
-    if rank == 0 and world == 1 and ref_bin.exists():
+    if rank == 0 and world == 1 and ref_bin.exists() and not args.no_reference_gpu:
         try:
             out = subprocess.run([str(ref_bin), "render", "400", "225", "100", "50", "/tmp/ref_cfg2.bin"], capture_output=True, text=True, timeout=120).stdout
             js = [l for l in out.splitlines() if l.startswith("REF_JSON")]

@@ -6,6 +6,11 @@
 //   ref_render render <w> <h> <spp> <depth> <out.bin>   raw w*h float4 framebuffer (post clamp+sqrt) + JSON timing
 //   ref_render scene <out.bin>                            the 488 spheres + raw material bytes SceneBook2BVH built
 //   ref_render rng <out.bin>                              cuHostRND(512,1984) stream and device XORWOW streams
+//   ref_render trace <rays.bin> <hits.bin>                the reference's own world->ClosestIntersection (BVH.cu:54-106 ->
+//                                                         SphereHittable.cu:56-66,91-102) + getNormal (:43-50,75-83) on a ray
+//                                                         file: n x rtb_ray (o.xyz, time, d.xyz, pad) in, n x 32-byte records
+//                                                         (t, normal.xyz, point.xyz, sphere index or -1) out
+#include <algorithm>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -80,6 +85,69 @@ static int cmd_scene(int argc, char** argv) {
 	return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+// One thread per ray through the reference's device object graph, exactly as sample_world does for one segment
+// (Renderer.cu:147-148): a fresh RayPayload, the world's virtual ClosestIntersection, then what a material would read
+// back: the distance, the geometry's getNormal, and in_ray.at(rec.distance) (cu_materials.cuh:58,83).
+struct TraceOut { float t, n[3], p[3]; int32_t index; const void* geom; };
+__global__ void trace_kernel(const Hittable* world, const float* rays, int n, TraceOut* out) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float* r = rays + 8 * (size_t)i;
+	Ray ray(glm::vec3(r[0], r[1], r[2]), glm::vec3(r[4], r[5], r[6]), r[3]);
+	RayPayload rec{};
+	bool hit = world->ClosestIntersection(ray, rec);
+	TraceOut o{}; o.t = rec.distance; o.index = -1; o.geom = nullptr;
+	if (hit) {
+		glm::vec3 nn = Sphere::getNormal(ray, rec);   // Sphere:: and MovingSphere::TraceRecord share one layout {ptr, normal}
+		glm::vec3 pp = ray.at(rec.distance);
+		o.n[0] = nn.x; o.n[1] = nn.y; o.n[2] = nn.z; o.p[0] = pp.x; o.p[1] = pp.y; o.p[2] = pp.z;
+		o.geom = reinterpret_cast<const Sphere::TraceRecord*>(&rec.payload)->sphere;
+	}
+	out[i] = o;
+}
+
+static int cmd_trace(int argc, char** argv) {
+	if (argc != 4) return 2;
+	FILE* f = fopen(argv[2], "rb"); if (!f) { perror("rays"); return 1; }
+	fseek(f, 0, SEEK_END); long bytes = ftell(f); fseek(f, 0, SEEK_SET);
+	int n = (int)(bytes / 32);
+	std::vector<float> rays(8 * (size_t)n);
+	if (fread(rays.data(), 32, n, f) != (size_t)n) return 1;
+	fclose(f);
+	SceneBook2BVH::Factory scene_factory{};
+	SceneBook2BVH* scene = scene_factory.MakeScene();
+	const SceneView* view = reinterpret_cast<const SceneView*>(scene);
+	cudaDeviceSetLimit(cudaLimitStackSize, 8192);   // as Renderer::Render does for the virtual calls (Renderer.cu:124)
+	float* d_rays; TraceOut* d_out;
+	cudaMalloc(&d_rays, rays.size() * 4); cudaMalloc(&d_out, sizeof(TraceOut) * (size_t)n);
+	cudaMemcpy(d_rays, rays.data(), rays.size() * 4, cudaMemcpyHostToDevice);
+	trace_kernel<<<(n + 63) / 64, 64>>>(scene->getWorldPtr(), d_rays, n, d_out);
+	cudaError_t e = cudaDeviceSynchronize();
+	if (e != cudaSuccess) { fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
+	std::vector<TraceOut> out(n);
+	cudaMemcpy(out.data(), d_out, sizeof(TraceOut) * (size_t)n, cudaMemcpyDeviceToHost);
+	// geometry pointer -> index of the sphere in construction order (SceneBook2BVH::sphere_handles)
+	std::vector<std::pair<const void*, int>> ptrs;
+	for (int i = 0; i < (int)view->sphere_handles.size(); ++i) {
+		const SphereHandleView* hv = reinterpret_cast<const SphereHandleView*>(&view->sphere_handles[i]);
+		ptrs.push_back({hv->moving_sphere_ptr ? (const void*)hv->moving_sphere_ptr : (const void*)hv->sphere_ptr, i});
+	}
+	std::sort(ptrs.begin(), ptrs.end());
+	FILE* o = fopen(argv[3], "wb"); if (!o) return 1;
+	int hits = 0;
+	for (int i = 0; i < n; ++i) {
+		if (out[i].geom) {
+			auto it = std::lower_bound(ptrs.begin(), ptrs.end(), std::make_pair(out[i].geom, -1));
+			if (it == ptrs.end() || it->first != out[i].geom) { fprintf(stderr, "unknown geometry pointer\n"); return 1; }
+			out[i].index = it->second; ++hits;
+		}
+		fwrite(&out[i], 32, 1, o);   // (t, n, p, index): the first 32 bytes of the record
+	}
+	fclose(o);
+	printf("REF_TRACE {\"rays\": %d, \"hits\": %d}\n", n, hits);
+	return 0;
+}
+
 static int cmd_rng(int argc, char** argv) {
 	if (argc != 3) return 2;
 	FILE* o = fopen(argv[2], "wb"); if (!o) return 1;
@@ -101,9 +169,10 @@ static int cmd_rng(int argc, char** argv) {
 }
 
 int main(int argc, char** argv) {
-	if (argc < 2) { fprintf(stderr, "usage: ref_render render|scene|rng ...\n"); return 2; }
+	if (argc < 2) { fprintf(stderr, "usage: ref_render render|scene|rng|trace ...\n"); return 2; }
 	if (!strcmp(argv[1], "render")) return cmd_render(argc, argv);
 	if (!strcmp(argv[1], "scene")) return cmd_scene(argc, argv);
 	if (!strcmp(argv[1], "rng")) return cmd_rng(argc, argv);
+	if (!strcmp(argv[1], "trace")) return cmd_trace(argc, argv);
 	return 2;
 }

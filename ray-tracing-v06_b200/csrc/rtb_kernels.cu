@@ -54,6 +54,23 @@ __device__ __forceinline__ void ldg8(const float4* p, float4& a, float4& b) {
 #endif
 }
 
+// Wavefront queue records are touched once per kernel: streaming (evict-first) loads and stores keep them from pushing
+// the BVH nodes and primitive records out of L1 / L2 (-DRTB_STREAM_HINTS=0: plain accesses).
+#ifndef RTB_STREAM_HINTS
+#define RTB_STREAM_HINTS 1
+#endif
+#if RTB_STREAM_HINTS
+__device__ __forceinline__ float4 ldq(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ int2 ldq(const int2* p) { return __ldcs(p); }
+__device__ __forceinline__ void stq(float4* p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ void stq(int2* p, int2 v) { __stcs(p, v); }
+#else
+__device__ __forceinline__ float4 ldq(const float4* p) { return *p; }
+__device__ __forceinline__ int2 ldq(const int2* p) { return *p; }
+__device__ __forceinline__ void stq(float4* p, float4 v) { *p = v; }
+__device__ __forceinline__ void stq(int2* p, int2 v) { *p = v; }
+#endif
+
 // Path id -> (global pixel index, absolute sample index).  Paths of a batch are laid out
 // sample-major: id = local_sample * npix + local_pixel, local pixels row-major from row_begin.
 __device__ __forceinline__ void path_pixel_sample(const BatchParams& bp, uint32_t batch, uint32_t path,
@@ -120,10 +137,10 @@ generate_kernel(BatchParams bp, rtb_camera cam, WaveView wv) {
 			d = rt::madd(cv, t, rt::madd(cu, s, cw));
 			if (cam.kind == RTB_CAM_MOTION) time = rt::mixf(cam.t0, cam.t1, r.z);
 		}
-		wv.ray_o[0][path] = make_float4(o.x, o.y, o.z, time);
-		wv.ray_d[0][path] = make_float4(d.x, d.y, d.z, __uint_as_float(path));
-		wv.thr[0][path] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-		wv.contrib[path] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		stq(wv.ray_o[0] + path, make_float4(o.x, o.y, o.z, time));
+		stq(wv.ray_d[0] + path, make_float4(d.x, d.y, d.z, __uint_as_float(path)));
+		stq(wv.thr[0] + path, make_float4(1.0f, 1.0f, 1.0f, 0.0f));
+		stq(wv.contrib + path, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
 	}
 }
 
@@ -304,6 +321,14 @@ __device__ __forceinline__ v3 xf_vec_to_world(const float4* tp, v3 v) {
 // `hit_code` is what a hit is reported on: the leaf itself, or for a box the quad record of the face that was hit.
 // (idx.. oiz: the ray's slab-test reciprocals, used to pick the faces of a box.)
 struct RaySlab { float idx, idy, idz, oix, oiy, oiz; };
+
+// Per-ray reciprocal of the slab tests.  A component that is (nearly) zero is nudged to +-1e-20 with the sign of the
+// component - signed zeros included, and every later sign decision is taken from the nudged value - so 0 * inf never appears.
+__device__ __forceinline__ float slab_dir(float d) { return fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d; }
+
+#ifndef RTB_UNIFIED_LEAF
+#define RTB_UNIFIED_LEAF 1
+#endif
 template <bool MEDIA>
 __device__ __forceinline__ float leaf_test(const SceneView& sv, int code, v3 o, v3 d, float a, float time, MediumRng& mr, float tbest,
                                            const RaySlab& rs, int& hit_code) {
@@ -312,6 +337,42 @@ __device__ __forceinline__ float leaf_test(const SceneView& sv, int code, v3 o, 
 	const float4* pp = sv.prims + 4 * (size_t)(code >> RTB_LEAF_TYPE_BITS);
 	const float4 q0 = ldg4(pp);
 	float t = FLT_MAX;
+#if RTB_UNIFIED_LEAF
+	// The lanes of a warp meet different flavours of the same shape (sphere / moving sphere / instanced sphere; box /
+	// instanced box): the instance transform and the moving centre are short predicated preludes, and the long part -
+	// the quadratic, the face tests - is ONE code path per shape that all those lanes run together.
+	const int base = type & 7;
+	if (MEDIA && (type == PRIM_MEDIUM_SPHERE || type == PRIM_MEDIUM_BOX)) {
+		const float4 q1 = ldg4(pp + 1);
+		if (type == PRIM_MEDIUM_SPHERE) return medium_sphere_hit(o, d, a, q0, q1.x, mr, __float_as_uint(q1.y), tbest);
+		const float4 q2 = ldg4(pp + 2), q3 = ldg4(pp + 3);
+		return medium_box_hit(o, d, a, q0, q1, q2, mr, __float_as_uint(q3.x), tbest);
+	}
+	const bool xf = (type & PRIM_XF) != 0;
+	v3 oo = o, dd = d; float a2 = a;
+	if (xf) {   // instance: take the ray into the primitive's frame (book translate::hit, rotate_y::hit)
+		xf_ray(pp + xf_offset(base), o, d, oo, dd);
+		a2 = rt::dot(dd, dd);
+	}
+	if (base <= PRIM_MOVING_SPHERE) {
+		v3 c = xyz(q0);
+		if (base == PRIM_MOVING_SPHERE) c = rt::mix(c, xyz(ldg4(pp + 1)), time);   // center = mix(center0, center1, ray.time)   SphereHittable.cu:92
+		t = sphere_closest(oo, dd, a2, c, q0.w);
+	} else if (base == PRIM_BOX) {
+		// the box in its own frame; when instanced, every record (the box's and each face's) is followed by the transform
+		RaySlab bs = rs;
+		if (xf) {
+			bs.idx = __frcp_rn(slab_dir(dd.x)); bs.idy = __frcp_rn(slab_dir(dd.y)); bs.idz = __frcp_rn(slab_dir(dd.z));
+			bs.oix = -(oo.x * bs.idx); bs.oiy = -(oo.y * bs.idy); bs.oiz = -(oo.z * bs.idz);
+		}
+		const int stride = xf ? 8 : 4;
+		int face;
+		t = box_hit(oo, dd, bs.idx, bs.idy, bs.idz, bs.oix, bs.oiy, bs.oiz, pp, q0, stride, tbest, face);
+		if (face >= 0) hit_code = (((code >> RTB_LEAF_TYPE_BITS) + (stride >> 2) * (1 + face)) << RTB_LEAF_TYPE_BITS) | PRIM_QUAD | (type & PRIM_XF);
+	} else {
+		t = planar_hit(oo, dd, pp, q0, base == PRIM_TRIANGLE, tbest);
+	}
+#else
 	if (type == PRIM_SPHERE) {
 		t = sphere_closest(o, d, a, xyz(q0), q0.w);
 	} else if (type == PRIM_MOVING_SPHERE) {
@@ -334,10 +395,7 @@ __device__ __forceinline__ float leaf_test(const SceneView& sv, int code, v3 o, 
 		else if (base == PRIM_MOVING_SPHERE) t = sphere_closest(oo, dd, a2, rt::mix(xyz(q0), xyz(ldg4(pp + 1)), time), q0.w);
 		else if (base == PRIM_BOX) {
 			// the box in its own frame; every record (the box's and each face's) is followed by the transform
-			const float gx = fabsf(dd.x) < 1e-20f ? copysignf(1e-20f, dd.x) : dd.x;
-			const float gy = fabsf(dd.y) < 1e-20f ? copysignf(1e-20f, dd.y) : dd.y;
-			const float gz = fabsf(dd.z) < 1e-20f ? copysignf(1e-20f, dd.z) : dd.z;
-			const float jx = __frcp_rn(gx), jy = __frcp_rn(gy), jz = __frcp_rn(gz);
+			const float jx = __frcp_rn(slab_dir(dd.x)), jy = __frcp_rn(slab_dir(dd.y)), jz = __frcp_rn(slab_dir(dd.z));
 			int face;
 			t = box_hit(oo, dd, jx, jy, jz, -(oo.x * jx), -(oo.y * jy), -(oo.z * jz), pp, q0, 8, tbest, face);
 			if (face >= 0) hit_code = (((code >> RTB_LEAF_TYPE_BITS) + 2 * (1 + face)) << RTB_LEAF_TYPE_BITS) | PRIM_QUAD | PRIM_XF;
@@ -352,11 +410,15 @@ __device__ __forceinline__ float leaf_test(const SceneView& sv, int code, v3 o, 
 			t = medium_box_hit(o, d, a, q0, q1, q2, mr, __float_as_uint(q3.x), tbest);
 		}
 	}
+#endif
 	return t;
 }
 
 #ifndef TRAV_WHILE_WHILE
 #define TRAV_WHILE_WHILE 1
+#endif
+#ifndef RTB_ROBUST_SLAB
+#define RTB_ROBUST_SLAB 1
 #endif
 #define TRAV_END ((int)0x80000000)
 
@@ -377,18 +439,25 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 		}
 		if (sv.bvh_empty) { tbest_out = tbest; code_out = best; return; }
 	}
-	// Slab test with a per-ray reciprocal; an exactly-zero component is nudged so 0 * inf never appears.
-	const float gx = fabsf(d.x) < 1e-20f ? copysignf(1e-20f, d.x) : d.x;
-	const float gy = fabsf(d.y) < 1e-20f ? copysignf(1e-20f, d.y) : d.y;
-	const float gz = fabsf(d.z) < 1e-20f ? copysignf(1e-20f, d.z) : d.z;
+	// Slab test with a per-ray reciprocal (slab_dir: zero components, signed zeros included, are nudged).
+	const float gx = slab_dir(d.x), gy = slab_dir(d.y), gz = slab_dir(d.z);
 	const float idx = __frcp_rn(gx), idy = __frcp_rn(gy), idz = __frcp_rn(gz);
 	const float oix = -(o.x * idx), oiy = -(o.y * idy), oiz = -(o.z * idz);
 	// Near / far slab planes are picked by the direction signs with FMAs instead of min/max pairs:
 	// t(min plane) = min * (1/d) - o/d, and the max plane adds ext * (1/d) on the side the sign says.
 	// (ncu: the min/max version kept the ALU pipe 66 % busy with the FMA pipe at 20 %.)
-	const float nx = d.x < 0.0f ? idx : 0.0f, fx = d.x < 0.0f ? 0.0f : idx;
-	const float ny = d.y < 0.0f ? idy : 0.0f, fy = d.y < 0.0f ? 0.0f : idy;
-	const float nz = d.z < 0.0f ? idz : 0.0f, fz = d.z < 0.0f ? 0.0f : idz;
+	// The sign is that of the value the reciprocal was taken of, so a -0.0 component picks the planes its -1e20 reciprocal needs.
+	const float nx = gx < 0.0f ? idx : 0.0f, fx = gx < 0.0f ? 0.0f : idx;
+	const float ny = gy < 0.0f ? idy : 0.0f, fy = gy < 0.0f ? 0.0f : idy;
+	const float nz = gz < 0.0f ? idz : 0.0f, fz = gz < 0.0f ? 0.0f : idz;
+#if RTB_ROBUST_SLAB
+	// The cull must never lose a box the exact primitive test would hit (aabb::intersects computes (min - o) / d, which
+	// cancels exactly; plane * (1/d) - o/d does not): the rounding of o/d is up to 2^-24 |o/d| per plane, the reciprocal and
+	// the two fused multiply-adds add a few 2^-24 of t.  The far distance is widened by both bounds before it is compared -
+	// one FMA per box; a box thinner than the rounding (a 1e-4 quad seen from 10,000 units) is then always entered.
+	const float slab_abs = 2.4e-7f * fmaxf(fmaxf(fabsf(oix), fabsf(oiy)), fabsf(oiz));   // 2 x 2^-23 max |o/d|
+	const float slab_rel = 1.0f + 9.6e-7f;                                                // 1 + 8 x 2^-23
+#endif
 
 #if RTB_NODE_PAIRED
 	const float2 id_xy = make_float2(idx, idy), oi_xy = make_float2(oix, oiy), n_xy = make_float2(nx, ny), f_xy = make_float2(fx, fy);
@@ -428,8 +497,14 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 			const float rtmax = fminf(fminf(fmaf(n2.y, fx, rx), fmaf(n2.z, fy, ry)), fmaf(n2.w, fz, rz));
 #endif
 			// aabb::intersects: tmin <= tmax && tmin < ray_max && tmax > 0   aabb.cuh:41
+#if RTB_ROBUST_SLAB
+			const float ltmax_c = fmaf(ltmax, slab_rel, slab_abs), rtmax_c = fmaf(rtmax, slab_rel, slab_abs);
+			const bool hl = ltmin <= ltmax_c && ltmin < tbest && ltmax_c > 0.0f;
+			const bool hr = rtmin <= rtmax_c && rtmin < tbest && rtmax_c > 0.0f;
+#else
 			const bool hl = ltmin <= ltmax && ltmin < tbest && ltmax > 0.0f;
 			const bool hr = rtmin <= rtmax && rtmin < tbest && rtmax > 0.0f;
+#endif
 			if (hl && hr) {
 				// nearer child next, farther child on the stack (BVH.cu:91-97); boxes that both contain
 				// the origin are ordered by where the ray leaves them
@@ -486,11 +561,11 @@ traverse_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
 	while (base < n) {
 		const uint32_t i = base + lane;
 		if (i < n) {
-			const float4 fo = ro[i], fd = rd[i];
+			const float4 fo = ldq(ro + i), fd = ldq(rd + i);
 			MediumRng mr = make_medium_rng(bp, batch, __float_as_uint(fd.w), bounce);
 			float t; int code;
 			trace_ray<MEDIA>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code);
-			wv.hit[i] = make_int2(__float_as_int(t), code);
+			stq(wv.hit + i, make_int2(__float_as_int(t), code));
 		}
 		__syncwarp();
 		if (n <= static_span) break;
@@ -760,8 +835,8 @@ shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
 		float4 no = make_float4(0, 0, 0, 0), nd = no; v3 nthr = rt::mk(0, 0, 0);
 		DeferredTex dt; dt.tex = -1; dt.u = dt.v = 0.0f; dt.p = rt::mk(0, 0, 0);
 		if (i < n) {
-			const float4 fo = ro[i], fd = rd[i], ft = rt_[i];
-			const int2 h = wv.hit[i];
+			const float4 fo = ldq(ro + i), fd = ldq(rd + i), ft = ldq(rt_ + i);
+			const int2 h = ldq(wv.hit + i);
 			alive = shade_segment<true>(sv, bp, wv, batch, bounce, fo, fd, xyz(ft), __int_as_float(h.x), h.y, no, nd, nthr, dt);
 		}
 		// live-path compaction: warp ballot/popc, one global atomic per block
@@ -778,7 +853,7 @@ shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
 		__syncthreads();
 		if (alive) {
 			const uint32_t pos = s_base + s_warp[warp] + __popc(mask & ((1u << lane) - 1u));
-			wo[pos] = no; wd[pos] = nd; wt[pos] = make_float4(nthr.x, nthr.y, nthr.z, 0.0f);
+			stq(wo + pos, no); stq(wd + pos, nd); stq(wt + pos, make_float4(nthr.x, nthr.y, nthr.z, 0.0f));
 			// texture work list: (p, queue slot), (u, v, -, texture id)
 			const bool defer = dt.tex >= 0;
 			const uint32_t act = __activemask();

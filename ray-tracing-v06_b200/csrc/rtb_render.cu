@@ -12,66 +12,18 @@
 #include <string>
 #include <vector>
 
-#include "rtb_kernels.h"
-#include "rtb_scene.h"
+#include "rtb_renderer.h"
 
 using namespace rtb;
-
-#define CUDA_TRY(expr)                                                                                  \
-	do {                                                                                                \
-		cudaError_t _e = (expr);                                                                        \
-		if (_e != cudaSuccess)                                                                          \
-			return fail(RTB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                 \
-	} while (0)
-
-struct rtb_renderer {
-	int device = 0;
-	cudaStream_t stream = nullptr;
-	cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
-	bool timed = false;
-
-	// scene arena
-	void* d_scene = nullptr; size_t scene_bytes = 0, scene_upload_bytes = 0;
-	SceneView sv{};
-	std::vector<uint8_t> staging;           // host copy of the arena of the last flattened scene
-	size_t off[7] = {0, 0, 0, 0, 0, 0, 0};
-	SceneView staged_sv{};
-	uint64_t staged_uid = 0, staged_version = 0;
-	bool has_scene = false;
-	rtb_scene_stats scene_stats{};
-	GpuScratch build_scratch;   // grow-only scratch of the GPU BVH build
-	uint64_t scene_version = 0;
-	rtb_camera cam{};
-	bool has_cam = false;
-
-	// framebuffers
-	uint32_t width = 0, height = 0;
-	float4 *d_accum = nullptr, *d_accum2 = nullptr, *d_out = nullptr;
-
-	// wavefront queues
-	void* d_wave = nullptr; size_t wave_paths = 0; uint32_t wave_depth = 0;
-	WaveView wv{};
-	LaunchCfg lc{};
-
-	// cached per-batch graph
-	cudaGraphExec_t graph_exec = nullptr;
-	BatchParams graph_bp{}; rtb_camera graph_cam{}; uint64_t graph_scene_version = 0; bool graph_valid = false;
-	float4 *graph_accum = nullptr;
-
-	uint64_t launches = 0, batches = 0;
-	uint32_t tail_threshold = 0;   // live-queue length below which the fused tail kernel takes a batch over
-
-	// optional per-launch event timing (rtb_renderer_set_profiling)
-	bool profiling = false;
-	std::vector<cudaEvent_t> prof_events;      // pairs (begin, end)
-	std::vector<int> prof_class;               // 0 generate, 1 traverse, 2 shade, 3 accumulate
-	size_t prof_used = 0;
-};
 
 static void prof_begin(rtb_renderer* r, int cls, cudaStream_t st) {
 	if (!r->profiling) return;
 	if (r->prof_used == r->prof_class.size()) {
-		cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+		cudaEvent_t a = nullptr, b = nullptr;
+		if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) {   // no events: this launch goes untimed
+			if (a) cudaEventDestroy(a);
+			cudaGetLastError(); r->profiling = false; return;
+		}
 		r->prof_events.push_back(a); r->prof_events.push_back(b); r->prof_class.push_back(cls);
 	}
 	r->prof_class[r->prof_used] = cls;
@@ -84,6 +36,8 @@ static void prof_end(rtb_renderer* r, cudaStream_t st) {
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int upload_staged_scene(rtb_renderer* r);
 
 static void free_graph(rtb_renderer* r) {
 	if (r->graph_exec) { cudaGraphExecDestroy(r->graph_exec); r->graph_exec = nullptr; }
@@ -111,11 +65,15 @@ int rtb_renderer_create(rtb_renderer** out, int device) {
 	CUDA_TRY(cudaSetDevice(device));
 	rtb_renderer* r = new rtb_renderer();
 	r->device = device;
-	CUDA_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
-	CUDA_TRY(cudaEventCreateWithFlags(&r->ev_in, cudaEventDisableTiming));
-	CUDA_TRY(cudaEventCreateWithFlags(&r->ev_out, cudaEventDisableTiming));
-	CUDA_TRY(cudaEventCreate(&r->ev_t0));
-	CUDA_TRY(cudaEventCreate(&r->ev_t1));
+	const int rc_init = [&]() -> int {   // (a failure past this point must not leak the half-built object)
+		CUDA_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+		CUDA_TRY(cudaEventCreateWithFlags(&r->ev_in, cudaEventDisableTiming));
+		CUDA_TRY(cudaEventCreateWithFlags(&r->ev_out, cudaEventDisableTiming));
+		CUDA_TRY(cudaEventCreate(&r->ev_t0));
+		CUDA_TRY(cudaEventCreate(&r->ev_t1));
+		return RTB_OK;
+	}();
+	if (rc_init != RTB_OK) { rtb_renderer_destroy(r); return rc_init; }
 	query_occupancy(device, r->lc);
 	r->tail_threshold = (uint32_t)r->lc.sms * 768u;   // ~6 warps of rays per SM sub-partition
 	if (const char* e = getenv("RTB_TAIL_THRESHOLD")) r->tail_threshold = (uint32_t)strtoul(e, nullptr, 10);
@@ -126,13 +84,14 @@ int rtb_renderer_create(rtb_renderer** out, int device) {
 void rtb_renderer_destroy(rtb_renderer* r) {
 	if (!r) return;
 	cudaSetDevice(r->device);
-	cudaStreamSynchronize(r->stream);
+	if (r->stream) cudaStreamSynchronize(r->stream);
 	free_graph(r);
 	free_gpu_scratch(r->build_scratch);
 	for (cudaEvent_t e : r->prof_events) cudaEventDestroy(e);
-	cudaFree(r->d_scene); cudaFree(r->d_accum); cudaFree(r->d_accum2); cudaFree(r->d_out); cudaFree(r->d_wave);
-	cudaEventDestroy(r->ev_in); cudaEventDestroy(r->ev_out); cudaEventDestroy(r->ev_t0); cudaEventDestroy(r->ev_t1);
-	cudaStreamDestroy(r->stream);
+	cudaFree(r->d_scene); cudaFree(r->d_accum); cudaFree(r->d_accum2); cudaFree(r->d_out); cudaFree(r->d_wave); cudaFree(r->d_rgb8);
+	for (cudaEvent_t e : {r->ev_in, r->ev_out, r->ev_t0, r->ev_t1}) if (e) cudaEventDestroy(e);
+	if (r->stream) cudaStreamDestroy(r->stream);
+	cudaGetLastError();
 	delete r;
 }
 
@@ -189,6 +148,34 @@ int rtb_renderer_set_scene(rtb_renderer* r, rtb_scene* s) {
 		r->staged_sv.bg_r = fs.background[0]; r->staged_sv.bg_g = fs.background[1]; r->staged_sv.bg_b = fs.background[2];
 		r->staged_uid = s->uid; r->staged_version = s->version;
 	}
+	const int rc_up = upload_staged_scene(r);
+	if (rc_up) return rc_up;
+	if (!cached) r->scene_version++;   // same bytes at the same addresses: the cached graph stays valid
+	return RTB_OK;
+}
+
+int rtb_renderer_share_scene(rtb_renderer* r, const rtb_renderer* src) {
+	if (!r || !src) return fail(RTB_ERR_INVALID, "rtb_renderer_share_scene: null argument");
+	if (src->staging.empty()) return fail(RTB_ERR_STATE, "rtb_renderer_share_scene: the source renderer has no scene");
+	if (r == src) return RTB_OK;
+	CUDA_TRY(cudaSetDevice(r->device));
+	const bool same = r->staged_uid == src->staged_uid && r->staged_version == src->staged_version && r->staging.size() == src->staging.size() && r->has_scene;
+	if (!same) {
+		r->staging = src->staging;
+		for (int i = 0; i < 7; ++i) r->off[i] = src->off[i];
+		r->staged_sv = src->staged_sv; r->staged_uid = src->staged_uid; r->staged_version = src->staged_version;
+		r->scene_stats = src->scene_stats;
+	}
+	const int rc_up = upload_staged_scene(r);
+	if (rc_up) return rc_up;
+	if (!same) r->scene_version++;
+	return RTB_OK;
+}
+
+}  // extern "C"
+
+// The staged arena -> device (one copy), and the device views of its sections.
+static int upload_staged_scene(rtb_renderer* r) {
 	const size_t total = r->staging.size();
 	CUDA_TRY(cudaStreamSynchronize(r->stream));
 	if (total > r->scene_bytes) {
@@ -208,9 +195,10 @@ int rtb_renderer_set_scene(rtb_renderer* r, rtb_scene* s) {
 	r->sv.pre_list = reinterpret_cast<const int32_t*>(base + r->off[6]);
 	r->has_scene = true;
 	r->scene_upload_bytes = total;
-	if (!cached) r->scene_version++;   // same bytes at the same addresses: the cached graph stays valid
 	return RTB_OK;
 }
+
+extern "C" {
 
 size_t rtb_renderer_scene_bytes(const rtb_renderer* r) { return r ? r->scene_upload_bytes : 0; }
 

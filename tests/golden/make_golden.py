@@ -11,7 +11,9 @@ Needs /root/reference (build container) for `make -C oracle ref`, and a GPU for 
   gpurun -- 'oracle/_ref/ref_render rng gpurun_out/ref_rng.bin;
              oracle/_ref/ref_render scene gpurun_out/ref_scene.bin;
              oracle/_ref/ref_render render 200 112 4 50 gpurun_out/ref_img_200x112_4spp_d50.bin;
-             oracle/_ref/ref_render render 400 225 100 50 gpurun_out/ref_img_400x225_100spp_d50.bin'
+             oracle/_ref/ref_render render 400 225 100 50 gpurun_out/ref_img_400x225_100spp_d50.bin;
+             oracle/_ref/ref_render trace oracle/_ref/trace_rays.bin gpurun_out/ref_trace.bin'
+     (after `python tests/golden/make_golden.py trace_rays` wrote oracle/_ref/trace_rays.bin, which travels to the box)
   python tests/golden/make_golden.py collect      # copies / converts gpurun_out/* into tests/golden/
 
 Fixtures:
@@ -19,6 +21,11 @@ Fixtures:
   ref_scene_book2_bouncing.bin             the 488 spheres + material bytes the reference's Scenes.cu built on the GPU box
   ref_megakernel_200x112_4spp_d50.bin      raw float4 framebuffer of the reference's render_kernel (first Render call)
   ref_megakernel_400x225_100spp_d50_f16.npy  same at config 2's size, stored as float16 RGB
+  ref_trace_book2_bouncing.npz             hit records (t, normal, point, sphere index) of the reference's own
+                                           world->ClosestIntersection + getNormal on the rays of helpers.reference_trace_rays
+  ref_sphere_index_host_1280x720.npz       (`python tests/golden/make_golden.py sphere_index`, CPU) the ground truth of the reference's
+                                           own unit test (google_testing/test.cpp:87-106) computed by the reference's
+                                           _sphere_closest_intersection + PinholeCamera (oracle/_ref/ref_sphere_index host)
   ref_bvh_book2_bouncing.bin               node array + primitive order of the reference's BuildBVH_TopDown
   oracle_images_32x18.npz                  (`python tests/golden/make_golden.py oracle`) the ORACLE's own Philox renders of every
                                            registered scene at 32x18, 2 spp, depth 8 - not a reference fixture: a tripwire that
@@ -61,6 +68,30 @@ def bvh():
     print("wrote", GOLD / "ref_bvh_book2_bouncing.bin")
 
 
+def sphere_index():
+    rtb = importlib.import_module("ray-tracing-v06_b200")
+    sys.path.insert(0, str(ROOT / "tests")); import helpers
+    idx, cam, _ = helpers.reference_sphere_index(rtb, "host", "/tmp")
+    np.savez_compressed(GOLD / "ref_sphere_index_host_1280x720.npz", index=idx.astype(np.int16).reshape(720, 1280), camera=cam)
+    print("wrote", GOLD / "ref_sphere_index_host_1280x720.npz")
+
+
+def trace_rays():
+    rtb = importlib.import_module("ray-tracing-v06_b200")
+    sys.path.insert(0, str(ROOT / "tests")); import helpers
+    rays = helpers.reference_trace_rays(rtb)
+    (ROOT / "oracle" / "_ref").mkdir(exist_ok=True)
+    rays.tofile(ROOT / "oracle" / "_ref" / "trace_rays.bin")
+    print("wrote", len(rays), "rays")
+
+
+def collect_trace():
+    sys.path.insert(0, str(ROOT / "tests")); import helpers
+    rec = np.fromfile(ROOT / "gpurun_out" / "ref_trace.bin", dtype=helpers.REF_TRACE_DTYPE)
+    np.savez_compressed(GOLD / "ref_trace_book2_bouncing.npz", t=rec["t"], n=rec["n"], p=rec["p"], index=rec["index"])
+    print("wrote", len(rec), "records,", int((rec["index"] >= 0).sum()), "hits")
+
+
 def collect():
     out = ROOT / "gpurun_out"
     shutil.copy(out / "ref_rng.bin", GOLD / "ref_rng.bin")
@@ -71,4 +102,4 @@ def collect():
 
 
 if __name__ == "__main__":
-    {"bvh": bvh, "collect": collect, "oracle": oracle_images}[sys.argv[1]]()
+    {"bvh": bvh, "collect": collect, "oracle": oracle_images, "trace_rays": trace_rays, "sphere_index": sphere_index, "collect_trace": collect_trace}[sys.argv[1]]()

@@ -42,27 +42,62 @@ def _compare_hits(rtb, g, o, exact=True, rtol=1e-5, max_tie_frac=0.01):
     return int(hit.sum())
 
 
-def test_sphere_index_recipe(rtb, orc, renderer):
-    """google_testing/test.cpp extended: scene recipe of SphereTest (static spheres, test camera, u = x/(W-1)*2-1),
-    closest-sphere index per pixel, GPU (BVH traversal) vs brute force — exact, all 921,600 pixels."""
-    src = rtb.Scene.named("book2_bouncing")
-    _, _, objs, _ = parse_blob(src.serialize())
-    spheres = [(o["f"][:3].copy(), float(o["f"][3])) for o in objs if o["kind"] in (0, 1)]   # moving spheres as static at center0 (test.cpp:38-40)
-    assert len(spheres) == 488
-    s = rtb.Scene(); m = s.lambertian(albedo=(0.5, 0.5, 0.5))
-    ids = [s.sphere(c, r, m) for c, r in spheres]
-    s.set_root(s.bvh(ids))
-    renderer.set_scene(s)
+def test_sphere_index_recipe(rtb, orc, renderer, tmp_path):
+    """google_testing/test.cpp (SphereTest.DeviceSphereIndexTest) extended to the new path: scene recipe of the test (488
+    static spheres), its camera and pixel mapping (u = x/(W-1)*2-1), closest-sphere index per pixel.  The truth is what the
+    REFERENCE's own _sphere_closest_intersection + PinholeCamera::sample_ray give (compiled from the reference's headers:
+    oracle/_ref/ref_sphere_index, golden tests/golden/ref_sphere_index_host_1280x720.npz; run live - host and, as the
+    reference's test does, device - when the binary travelled with the repo).  The GPU traces the very rays the reference
+    built, through its BVH: equal on all 921,600 pixels, except where a sphere is grazed within float32 rounding (the
+    reference's host code, its device code and the arithmetic spec contract multiply-adds differently; the reference's own
+    host-vs-device EXPECT_EQ is subject to the same handful of pixels)."""
+    from conftest import GOLDEN, ROOT
+    from helpers import grazing_only, reference_sphere_index, test_spheres
     W, H = 1280, 720
+    sp = test_spheres(rtb)
+    s = rtb.Scene(); m = s.lambertian(albedo=(0.5, 0.5, 0.5))
+    s.set_root(s.bvh([s.sphere(c[:3], float(c[3]), m) for c in sp]))
+    renderer.set_scene(s)
     cam = rtb.make_camera("pinhole", (0, 1, -4), (0, 1, 0), (0, 1, 0), 90.0, W / H)
+    gold = np.load(GOLDEN / "ref_sphere_index_host_1280x720.npz")
+    assert np.array_equal(np.array([*cam.o, *cam.u, *cam.v, *cam.w], dtype=np.float32), gold["camera"])
     rays = camera_rays(rtb, cam, W, H, "test")
+    truths = {"golden(host)": gold["index"].reshape(-1).astype(np.int32)}
+    if (ROOT / "oracle" / "_ref" / "ref_sphere_index").exists():
+        for mode in ("host", "device"):
+            idx, cam12, ref_rays = reference_sphere_index(rtb, mode, tmp_path, W, H)
+            assert np.array_equal(cam12, gold["camera"])
+            if mode == "host":
+                assert np.array_equal(ref_rays["d"].view(np.uint32), rays["d"].view(np.uint32)) and np.array_equal(ref_rays["o"], rays["o"])
+                assert np.array_equal(idx, truths["golden(host)"])
+            truths[mode] = idx
     hits = renderer.trace_rays(rays)
-    truth = orc.sphere_index_image(np.array([[*c, r] for c, r in spheres], dtype=np.float32), cam, W, H).reshape(-1)
-    # camera_rays builds d = w + u*s + v*t with numpy (no fma); compare only where the oracle's own ray agrees
-    o_hits = _oracle_scene(orc, s).trace_rays(rays, rtb.HIT_DTYPE)
-    assert np.array_equal(hits["object"], o_hits["object"])
-    agree = float((hits["object"] == truth).mean())
-    assert agree > 0.9999, f"closest-sphere index agrees on {agree:.6f} of pixels"
+    got = hits["object"]
+    assert np.array_equal(got, _oracle_scene(orc, s).trace_rays(rays, rtb.HIT_DTYPE)["object"])     # GPU == oracle, all pixels
+    for name, truth in truths.items():
+        bad = np.nonzero(got != truth)[0]
+        print(f"sphere index vs reference {name}: {len(bad)} of {W * H} pixels differ")
+        assert len(bad) <= 16
+        assert grazing_only(rays[bad], sp, got[bad], truth[bad]).all(), f"{name}: a differing pixel is not a grazing tie"
+    if "device" in truths:   # the reference's own test on this box, for the record
+        own = np.nonzero(truths["host"] != truths["device"])[0]
+        print(f"reference host vs reference device (its own EXPECT_EQ): {len(own)} pixels differ")
+        assert grazing_only(rays[own], sp, truths["host"][own], truths["device"][own]).all()
+
+
+def test_hit_records_match_reference_device(rtb, renderer):
+    """Per-ray hit records against the reference's own DEVICE code - world->ClosestIntersection (BVH.cu:54-106 ->
+    SphereHittable.cu:56-66,91-102) and getNormal, run on a B200 over 102,400 rays (oracle/_ref/ref_render trace;
+    tests/golden/ref_trace_book2_bouncing.npz): rtb_trace_rays on the same rays must name the same sphere, with t, point
+    and normal inside the binary32 rounding bound of the reference's formula (helpers.check_against_reference_trace says
+    why north_star's flat 1e-5 cannot be the bar on the r = 1000 sphere, and checks it where it can)."""
+    from conftest import GOLDEN
+    from helpers import check_against_reference_trace, reference_trace_rays
+    rays = reference_trace_rays(rtb)
+    scene = rtb.Scene.named("book2_bouncing")
+    renderer.set_scene(scene)
+    got = renderer.trace_rays(rays)
+    print("reference device hit records:", check_against_reference_trace(rtb, rays, got, np.load(GOLDEN / "ref_trace_book2_bouncing.npz")))
 
 
 @pytest.mark.parametrize("name,lo,hi", [("book2_bouncing", -12, 12), ("book1_final", -12, 12), ("book2_quads", -6, 9)])
@@ -517,3 +552,69 @@ def test_scene_and_size_switching(rtb, renderer):
         if key in ref:
             assert np.array_equal(ref[key], img), key
         ref[key] = img
+
+
+def test_signed_zero_and_axis_parallel_directions(rtb, orc, renderer):
+    """Direction components of exactly +0.0 and -0.0 (numpy's `-np.array([0, 0, 1])` is (-0, -0, -1)): the slab test takes
+    every sign decision from the value it took the reciprocal of, so such rays - from inside and outside the boxes - walk
+    the tree like any other (aabb::intersects, aabb.cuh:30-44, gives -inf..+inf on such an axis)."""
+    for name, lo, hi in (("book2_bouncing", -8.0, 8.0), ("book2_final", -100.0, 500.0), ("book2_cornell", 50.0, 500.0)):
+        scene = rtb.Scene.named(name)
+        renderer.set_scene(scene)
+        rng = np.random.default_rng(99)
+        n = 30_000
+        rays = np.zeros(n, dtype=rtb.RAY_DTYPE)
+        rays["o"] = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+        if name == "book2_bouncing":
+            rays["o"][:, 1] = rng.uniform(0.05, 3.0, n).astype(np.float32)
+        d = rng.normal(size=(n, 3)).astype(np.float32)
+        zero = rng.integers(0, 7, n)                      # which components are zeroed (never all three)
+        sign = rng.integers(0, 2, (n, 3)).astype(bool)
+        for k in range(3):
+            z = ((zero >> k) & 1).astype(bool)
+            d[z, k] = np.where(sign[z, k], np.float32(-0.0), np.float32(0.0))
+        rays["d"] = d; rays["time"] = rng.random(n).astype(np.float32)
+        assert (np.signbit(rays["d"]) & (rays["d"] == 0)).sum() > 1000
+        g = renderer.trace_rays(rays)
+        o = _oracle_scene(orc, scene).trace_rays(rays, rtb.HIT_DTYPE)
+        assert _compare_hits(rtb, g, o, exact=True, max_tie_frac=0.02) > 3_000
+
+
+def test_thin_far_geometry_is_never_culled(rtb, orc, renderer):
+    """Quads (zero thickness; 1e-4 of padding in the BVH, which vanishes in float32 beyond 1,000 units) and 1e-4-thick boxes
+    1,000 to 10,000 units from the rays' origins, seen face-on, obliquely and edge-on: the reference's slab test
+    ((min - o) / d, aabb.cuh:30-44) keeps such boxes, and the product's reciprocal form widens the far distance by its
+    rounding bound so that it does too.  The oracle scans the list without any BVH: every hit must be found, bit for bit."""
+    rng = np.random.default_rng(4)
+    s = rtb.Scene(); m = s.lambertian(albedo=(0.5, 0.5, 0.5))
+    objs = []; targets = []
+    for k in range(300):
+        dist = float(rng.uniform(1000.0, 10000.0))
+        dirn = rng.normal(size=3); dirn /= np.linalg.norm(dirn)
+        c = (dirn * dist).astype(np.float32)
+        axis = int(rng.integers(0, 3))
+        u = np.zeros(3, dtype=np.float32); v = np.zeros(3, dtype=np.float32)
+        u[(axis + 1) % 3] = rng.uniform(0.5, 4.0); v[(axis + 2) % 3] = rng.uniform(0.5, 4.0)
+        if k % 3 == 2:      # a 1e-4-thick slab
+            a = c.copy(); b = c + u + v; b[axis] = a[axis] + np.float32(1e-4)
+            objs.append(s.box(a, b, m))
+        else:
+            objs.append(s.quad(c, u, v, m))
+        targets.append((c, u, v))
+    s.set_root(s.list(objs))
+    renderer.set_scene(s)
+    n_per = 200
+    rays = np.zeros(len(targets) * n_per, dtype=rtb.RAY_DTYPE)
+    for k, (c, u, v) in enumerate(targets):
+        a = rng.random((n_per, 1)).astype(np.float32); b = rng.random((n_per, 1)).astype(np.float32)
+        tgt = c[None, :] + u[None, :] * a + v[None, :] * b
+        o = rng.uniform(-5.0, 5.0, (n_per, 3)).astype(np.float32)
+        scale = rng.choice(np.array([1.0, 1e-3, 37.0], dtype=np.float32), (n_per, 1))     # un-normalised directions of several lengths
+        rays["o"][k * n_per:(k + 1) * n_per] = o
+        rays["d"][k * n_per:(k + 1) * n_per] = (tgt - o) * scale
+    g = renderer.trace_rays(rays)
+    o_hits = _oracle_scene(orc, s).trace_rays(rays, rtb.HIT_DTYPE)
+    assert (o_hits["object"] >= 0).mean() > 0.5
+    lost = (o_hits["object"] >= 0) & (g["object"] < 0)
+    assert not lost.any(), f"{lost.sum()} hits of the oracle were culled by the slab test"
+    assert _compare_hits(rtb, g, o_hits, exact=True, max_tie_frac=0.02) > 20_000
