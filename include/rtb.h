@@ -240,6 +240,22 @@ int  rtb_resolve(rtb_renderer* r, void* d_out, void* stream);
 int  rtb_download(rtb_renderer* r, float* host_rgba);
 /* Raw accumulators (rgb sums + count) and sums of squares; either pointer may be NULL. */
 int  rtb_download_accum(rtb_renderer* r, float* host_sum, float* host_sum2);
+/* Output stage of FirstApp::write_renderbuffer (main/src/FirstApp.cpp:108-122) on the device: the resolved image
+ * quantised as uint8 = value * 255.999f, RGB only, rows flipped when flip_rows != 0 (row 0 of the float buffer is the
+ * bottom of the picture; stbi_flip_vertically_on_write(true) in the reference); host_rgb holds w*h*3 bytes. */
+int  rtb_download_rgb8(rtb_renderer* r, uint8_t* host_rgb, int flip_rows);
+/* Uploads to `r` the scene that `src` (a renderer on another device) flattened in its last rtb_renderer_set_scene:
+ * one flatten, N uploads (what rtb_multi_set_scene does). */
+int  rtb_renderer_share_scene(rtb_renderer* r, const rtb_renderer* src);
+
+/* Progressive rendering across process lifetimes: a checkpoint holds the radiance sums, the sums of squares and the
+ * sample cursor (one past the last sample index accumulated since the last RTB_RENDER_CLEAR).  A render continued
+ * from a loaded checkpoint - rtb_render with sample_begin = the cursor and without RTB_RENDER_CLEAR - is bit-identical
+ * to the uninterrupted one.  (The reference overwrites its output buffer on every Render(), Renderer.cu:216; its RNG
+ * state persists instead - with counter-based streams the sample cursor is the whole state.) */
+int  rtb_save_accum(rtb_renderer* r, const char* path);
+int  rtb_load_accum(rtb_renderer* r, const char* path, uint32_t* width_out, uint32_t* height_out, uint32_t* sample_cursor_out);
+uint32_t rtb_renderer_sample_cursor(const rtb_renderer* r);
 int  rtb_get_counters(rtb_renderer* r, rtb_counters* out);
 
 /* Per-kernel-class device time, measured with CUDA events around every launch on the stream the
@@ -253,6 +269,10 @@ typedef struct rtb_profile {
 } rtb_profile;
 int  rtb_renderer_set_profiling(rtb_renderer* r, int on);
 int  rtb_get_profile(rtb_renderer* r, rtb_profile* out);   /* synchronizes; totals since the last call */
+/* The individual launches behind rtb_get_profile, in launch order (call it BEFORE rtb_get_profile, which resets):
+ * ms_out[i] = device time, class_out[i] = 0 generate, 1 traverse, 2 shade (+ texture), 3 accumulate, 4 tail check.
+ * Returns the number of launches recorded (may exceed cap). */
+int  rtb_get_profile_launches(rtb_renderer* r, float* ms_out, int32_t* class_out, int cap);
 int  rtb_reset_counters(rtb_renderer* r);
 /* Live-queue length at every bounce of the LAST batch rendered (out[b], b < cap); returns max_depth. */
 int  rtb_queue_lengths(rtb_renderer* r, uint32_t* out, int cap);
@@ -278,6 +298,41 @@ typedef struct rtb_hit {                                                        
 /* Closest hits for n host rays through the traversal code of the wavefront (media are skipped: they are
  * stochastic), with the full hit record materials would see and per-ray traversal statistics. */
 int rtb_trace_rays(rtb_renderer* r, const rtb_ray* rays, size_t n, rtb_hit* hits_out);
+
+/* ------------------------------------------------------------------ several GPUs of one box
+ *
+ * The reference renders on one device (main/src/FirstApp.cpp:39-40,94-101).  An rtb_multi_renderer drives one
+ * rtb_renderer per device from a single process: the scene is flattened once and uploaded to every device, a render's
+ * sample range [sample_begin, sample_end) is split into contiguous sub-ranges (device i of n renders
+ * [begin + spp*i/n, begin + spp*(i+1)/n) of every pixel - perfectly balanced, and with counter-based random streams the
+ * very samples one device would have drawn), all devices render concurrently, and the per-device radiance sums are
+ * summed onto the first device: one ncclReduce(sum) per render over NVLink (NCCL is loaded at run time, libnccl.so.2),
+ * or - RTB_REDUCE_P2P - one kernel on the first device that reads its peers' accumulators through peer memory and adds
+ * them in device order (bit-reproducible).  rtb_multi_download then resolves and copies from the first device. */
+typedef struct rtb_multi_renderer rtb_multi_renderer;
+enum rtb_multi_reduce { RTB_REDUCE_AUTO = 0, RTB_REDUCE_NCCL = 1, RTB_REDUCE_P2P = 2 };
+
+/* devices = n CUDA device indices (NULL: devices 0..n-1). */
+int  rtb_multi_renderer_create(rtb_multi_renderer** out, const int* devices, int n, int reduce_mode);
+void rtb_multi_renderer_destroy(rtb_multi_renderer* m);
+int  rtb_multi_device_count(const rtb_multi_renderer* m);
+/* The renderer of device slot i (counters, profiling, scene statistics); owned by m. */
+rtb_renderer* rtb_multi_renderer_get(rtb_multi_renderer* m, int i);
+/* RTB_REDUCE_NCCL or RTB_REDUCE_P2P: what this object uses (AUTO picks NCCL when it loads, else peer memory). */
+int  rtb_multi_reduce_mode(const rtb_multi_renderer* m);
+int  rtb_multi_set_scene(rtb_multi_renderer* m, rtb_scene* s);
+int  rtb_multi_set_camera(rtb_multi_renderer* m, const rtb_camera* cam);
+/* Asynchronous.  Without RTB_RENDER_CLEAR the new samples are added to what every device holds (progressive). */
+int  rtb_multi_render(rtb_multi_renderer* m, const rtb_render_params* p);
+int  rtb_multi_synchronize(rtb_multi_renderer* m);
+/* Resolve of the cross-device total + blocking copy, as rtb_download / rtb_download_accum / rtb_download_rgb8. */
+int  rtb_multi_download(rtb_multi_renderer* m, float* host_rgba);
+int  rtb_multi_download_accum(rtb_multi_renderer* m, float* host_sum, float* host_sum2);
+int  rtb_multi_download_rgb8(rtb_multi_renderer* m, uint8_t* host_rgb, int flip_rows);
+/* paths, rays, launches, batches summed over the devices; render_ms = device time of the last rtb_multi_render from the
+ * first launch to the end of the reduction, the slowest device (valid after rtb_multi_synchronize). */
+int  rtb_multi_get_counters(rtb_multi_renderer* m, rtb_counters* out);
+int  rtb_multi_reset_counters(rtb_multi_renderer* m);
 
 #ifdef __cplusplus
 }

@@ -30,6 +30,8 @@ WORLD_BVH_QUALITY, WORLD_BVH_AS_BUILT, WORLD_BVH_GPU_LBVH = 0, 1, 2
 BUILDER_NAMES = {0: "host_sah", 1: "as_built", 2: "gpu_lbvh", 3: "host_median_fallback"}
 CAM_PINHOLE, CAM_DEFOCUS, CAM_MOTION = 0, 1, 2
 RENDER_CLEAR, RENDER_VARIANCE = 1, 2
+REDUCE_AUTO, REDUCE_NCCL, REDUCE_P2P = 0, 1, 2
+PROFILE_CLASSES = {0: "generate", 1: "traverse", 2: "shade", 3: "accumulate", 4: "tail"}
 MISS_DIST = np.float32(3.402823466e38)
 
 
@@ -147,6 +149,26 @@ ABI = {
     "rtb_renderer_set_profiling": (C.c_int, [_P, C.c_int]),
     "rtb_get_profile": (C.c_int, [_P, C.POINTER(Profile)]),
     "rtb_trace_rays": (C.c_int, [_P, _P, C.c_size_t, _P]),
+    "rtb_download_rgb8": (C.c_int, [_P, _P, C.c_int]),
+    "rtb_renderer_share_scene": (C.c_int, [_P, _P]),
+    "rtb_save_accum": (C.c_int, [_P, C.c_char_p]),
+    "rtb_load_accum": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "rtb_renderer_sample_cursor": (C.c_uint32, [_P]),
+    "rtb_get_profile_launches": (C.c_int, [_P, _P, _P, C.c_int]),
+    "rtb_multi_renderer_create": (C.c_int, [C.POINTER(_P), C.POINTER(C.c_int), C.c_int, C.c_int]),
+    "rtb_multi_renderer_destroy": (None, [_P]),
+    "rtb_multi_device_count": (C.c_int, [_P]),
+    "rtb_multi_renderer_get": (_P, [_P, C.c_int]),
+    "rtb_multi_reduce_mode": (C.c_int, [_P]),
+    "rtb_multi_set_scene": (C.c_int, [_P, _P]),
+    "rtb_multi_set_camera": (C.c_int, [_P, C.POINTER(Camera)]),
+    "rtb_multi_render": (C.c_int, [_P, C.POINTER(RenderParams)]),
+    "rtb_multi_synchronize": (C.c_int, [_P]),
+    "rtb_multi_download": (C.c_int, [_P, _P]),
+    "rtb_multi_download_accum": (C.c_int, [_P, _P, _P]),
+    "rtb_multi_download_rgb8": (C.c_int, [_P, _P, C.c_int]),
+    "rtb_multi_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
+    "rtb_multi_reset_counters": (C.c_int, [_P]),
 }
 SCENES_ABI = {
     "rtb_scenes_count": (C.c_int, []),
@@ -425,6 +447,35 @@ class Renderer:
         _check(lib().rtb_trace_rays(self.handle, r.ctypes.data, r.shape[0], hits.ctypes.data), "rtb_trace_rays")
         return hits
 
+    def download_rgb8(self, flip_rows: bool = True) -> np.ndarray:
+        """The 8-bit image FirstApp::write_renderbuffer writes (x * 255.999, RGB, rows flipped), quantised on the device."""
+        out = np.empty((self.height, self.width, 3), dtype=np.uint8)
+        _check(lib().rtb_download_rgb8(self.handle, out.ctypes.data, 1 if flip_rows else 0), "rtb_download_rgb8")
+        return out
+
+    def share_scene(self, src: "Renderer"):
+        _check(lib().rtb_renderer_share_scene(self.handle, src.handle), "rtb_renderer_share_scene")
+
+    def save_accum(self, path):
+        _check(lib().rtb_save_accum(self.handle, str(path).encode()), "rtb_save_accum")
+
+    def load_accum(self, path) -> int:
+        """Loads a checkpoint; returns the sample cursor (pass it as sample_begin with clear=False to continue)."""
+        w, h, cur = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        _check(lib().rtb_load_accum(self.handle, str(path).encode(), C.byref(w), C.byref(h), C.byref(cur)), "rtb_load_accum")
+        self.width, self.height = int(w.value), int(h.value)
+        return int(cur.value)
+
+    def sample_cursor(self) -> int:
+        return int(lib().rtb_renderer_sample_cursor(self.handle))
+
+    def profile_launches(self, cap: int = 4096):
+        """(ms, class) of every launch of the profiled renders since the last profile() call, in launch order."""
+        ms = np.zeros(cap, dtype=np.float32); cls = np.zeros(cap, dtype=np.int32)
+        n = _check(lib().rtb_get_profile_launches(self.handle, ms.ctypes.data, cls.ctypes.data, cap), "rtb_get_profile_launches")
+        n = min(n, cap)
+        return ms[:n].copy(), cls[:n].copy()
+
     def accum_tensor(self):
         """The device accumulator as a torch tensor (H, W, 4) sharing memory — used for the NCCL reduce."""
         import torch
@@ -434,3 +485,69 @@ class Renderer:
         w = _Wrap()
         w.__cuda_array_interface__ = {"shape": (self.height, self.width, 4), "typestr": "<f4", "data": (self.accum_ptr(), False), "version": 3}
         return torch.as_tensor(w, device=f"cuda:{self.device}")
+
+
+class MultiRenderer:
+    """Owns an rtb_multi_renderer*: one process, several GPUs of one box (sample-range partition + one reduce)."""
+
+    def __init__(self, devices, reduce=REDUCE_AUTO):
+        devs = list(range(devices)) if isinstance(devices, int) else list(devices)
+        arr = (C.c_int * len(devs))(*devs)
+        h = _P()
+        _check(lib().rtb_multi_renderer_create(C.byref(h), arr, len(devs), reduce), "rtb_multi_renderer_create")
+        self.handle = h.value
+        self.devices = devs
+        self.width = self.height = 0
+        self._scene = None
+
+    def __del__(self):
+        if getattr(self, "handle", None) and _lib is not None:
+            _lib.rtb_multi_renderer_destroy(self.handle)
+            self.handle = None
+
+    @property
+    def reduce_mode(self) -> str:
+        return {REDUCE_NCCL: "nccl", REDUCE_P2P: "p2p"}.get(lib().rtb_multi_reduce_mode(self.handle), "?")
+
+    def set_scene(self, scene: Scene):
+        _check(lib().rtb_multi_set_scene(self.handle, scene.handle), "rtb_multi_set_scene")
+        self._scene = scene
+
+    def set_camera(self, cam: Camera):
+        _check(lib().rtb_multi_set_camera(self.handle, C.byref(cam)), "rtb_multi_set_camera")
+
+    def render(self, width, height, sample_begin, sample_end, max_depth, seed=1984, clear=True, variance=False, samples_per_batch=0):
+        p = RenderParams(width, height, sample_begin, sample_end, 0, 0, max_depth, seed,
+                         (RENDER_CLEAR if clear else 0) | (RENDER_VARIANCE if variance else 0), samples_per_batch)
+        _check(lib().rtb_multi_render(self.handle, C.byref(p)), "rtb_multi_render")
+        self.width, self.height = width, height
+
+    def synchronize(self):
+        _check(lib().rtb_multi_synchronize(self.handle), "rtb_multi_synchronize")
+
+    def download(self) -> np.ndarray:
+        out = np.empty((self.height, self.width, 4), dtype=np.float32)
+        _check(lib().rtb_multi_download(self.handle, out.ctypes.data), "rtb_multi_download")
+        return out
+
+    def download_into(self, host_ptr: int):
+        _check(lib().rtb_multi_download(self.handle, host_ptr), "rtb_multi_download")
+
+    def download_accum(self, want_sum2=False):
+        s = np.empty((self.height, self.width, 4), dtype=np.float32)
+        s2 = np.empty_like(s) if want_sum2 else None
+        _check(lib().rtb_multi_download_accum(self.handle, s.ctypes.data, s2.ctypes.data if want_sum2 else None), "rtb_multi_download_accum")
+        return (s, s2) if want_sum2 else s
+
+    def download_rgb8(self, flip_rows: bool = True) -> np.ndarray:
+        out = np.empty((self.height, self.width, 3), dtype=np.uint8)
+        _check(lib().rtb_multi_download_rgb8(self.handle, out.ctypes.data, 1 if flip_rows else 0), "rtb_multi_download_rgb8")
+        return out
+
+    def counters(self) -> Counters:
+        c = Counters()
+        _check(lib().rtb_multi_get_counters(self.handle, C.byref(c)), "rtb_multi_get_counters")
+        return c
+
+    def reset_counters(self):
+        _check(lib().rtb_multi_reset_counters(self.handle), "rtb_multi_reset_counters")

@@ -54,10 +54,12 @@ __device__ __forceinline__ void ldg8(const float4* p, float4& a, float4& b) {
 #endif
 }
 
-// Wavefront queue records are touched once per kernel: streaming (evict-first) loads and stores keep them from pushing
-// the BVH nodes and primitive records out of L1 / L2 (-DRTB_STREAM_HINTS=0: plain accesses).
+// Wavefront queue records are touched once per kernel.  -DRTB_STREAM_HINTS=1 marks those accesses streaming (evict-first,
+// ld/st.global.cs) to keep them from pushing BVH nodes and primitive records out of L1 / L2.  Measured on B200 (round 2):
+// traverse 28.4 vs 28.5 ms per step, shade 11.9 vs 11.4 ms - the queues are not what evicts the tree, and shade's stores
+// do better write-back cached.  Off by default.
 #ifndef RTB_STREAM_HINTS
-#define RTB_STREAM_HINTS 1
+#define RTB_STREAM_HINTS 0
 #endif
 #if RTB_STREAM_HINTS
 __device__ __forceinline__ float4 ldq(const float4* p) { return __ldcs(p); }
@@ -498,7 +500,12 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 #endif
 			// aabb::intersects: tmin <= tmax && tmin < ray_max && tmax > 0   aabb.cuh:41
 #if RTB_ROBUST_SLAB
+#if RTB_NODE_PAIRED
+			const float2 tmax_c = __ffma2_rn(make_float2(ltmax, rtmax), make_float2(slab_rel, slab_rel), make_float2(slab_abs, slab_abs));
+			const float ltmax_c = tmax_c.x, rtmax_c = tmax_c.y;
+#else
 			const float ltmax_c = fmaf(ltmax, slab_rel, slab_abs), rtmax_c = fmaf(rtmax, slab_rel, slab_abs);
+#endif
 			const bool hl = ltmin <= ltmax_c && ltmin < tbest && ltmax_c > 0.0f;
 			const bool hr = rtmin <= rtmax_c && rtmin < tbest && rtmax_c > 0.0f;
 #else
@@ -985,6 +992,20 @@ resolve_kernel(const float4* __restrict__ accum, float4* __restrict__ out, uint3
 	}
 }
 
+// Output stage of FirstApp::write_renderbuffer (FirstApp.cpp:108-122) on the device: mean -> clamp -> sqrt (as resolve),
+// uint8 = value * 255.999f, RGB, optionally with the rows flipped (the float buffer's row 0 is the bottom of the picture).
+__global__ void __launch_bounds__(STREAM_THREADS)
+quantize_kernel(const float4* __restrict__ accum, uint8_t* __restrict__ rgb, uint32_t width, uint32_t height, int flip_rows) {
+	const uint32_t n = width * height, stride = gridDim.x * blockDim.x;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const uint32_t y = i / width, x = i - y * width;
+		const float4 a = accum[(size_t)(flip_rows ? height - 1 - y : y) * width + x];
+		const float inv = 1.0f / a.w;
+		const float r = sqrtf(fminf(fmaxf(a.x * inv, 0.0f), 1.0f)), g = sqrtf(fminf(fmaxf(a.y * inv, 0.0f), 1.0f)), b = sqrtf(fminf(fmaxf(a.z * inv, 0.0f), 1.0f));
+		rgb[3 * (size_t)i] = (uint8_t)(r * 255.999f); rgb[3 * (size_t)i + 1] = (uint8_t)(g * 255.999f); rgb[3 * (size_t)i + 2] = (uint8_t)(b * 255.999f);
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // hit-record parity hook
 
@@ -1105,6 +1126,11 @@ void launch_accumulate(const BatchParams& bp, const WaveView& wv, float4* accum,
 void launch_resolve(const float4* accum, float4* out, uint32_t n, cudaStream_t st) {
 	int blocks = (int)((n + STREAM_THREADS - 1) / STREAM_THREADS); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
 	resolve_kernel<<<blocks, STREAM_THREADS, 0, st>>>(accum, out, n);
+}
+void launch_quantize(const float4* accum, uint8_t* rgb, uint32_t width, uint32_t height, int flip_rows, cudaStream_t st) {
+	const uint32_t n = width * height;
+	int blocks = (int)((n + STREAM_THREADS - 1) / STREAM_THREADS); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+	quantize_kernel<<<blocks, STREAM_THREADS, 0, st>>>(accum, rgb, width, height, flip_rows);
 }
 void launch_trace_rays(const SceneView& sv, const float4* ray_o, const float4* ray_d, uint32_t n, int2* hit_tmp, int2* stats_tmp,
                        rtb_hit* hits_out, uint32_t* work_counter, const LaunchCfg& lc, cudaStream_t st) {

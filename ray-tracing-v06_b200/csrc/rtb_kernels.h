@@ -66,6 +66,7 @@ void launch_shade(const SceneView& sv, const BatchParams& bp, const WaveView& wv
 void launch_texture(const SceneView& sv, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st);
 void launch_accumulate(const BatchParams& bp, const WaveView& wv, float4* accum, float4* accum2, const LaunchCfg& lc, cudaStream_t st);
 void launch_resolve(const float4* accum, float4* out, uint32_t n, cudaStream_t st);
+void launch_quantize(const float4* accum, uint8_t* rgb, uint32_t width, uint32_t height, int flip_rows, cudaStream_t st);
 
 // Parity hook: closest hits + full hit records for explicit rays (media skipped).
 void launch_trace_rays(const SceneView& sv, const float4* ray_o, const float4* ray_d, uint32_t n, int2* hit_tmp, int2* stats_tmp,

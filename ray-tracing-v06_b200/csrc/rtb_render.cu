@@ -146,6 +146,7 @@ int rtb_renderer_set_scene(rtb_renderer* r, rtb_scene* s) {
 		}
 		r->staged_sv.background_mode = fs.background_mode;
 		r->staged_sv.bg_r = fs.background[0]; r->staged_sv.bg_g = fs.background[1]; r->staged_sv.bg_b = fs.background[2];
+		for (int k = 0; k < 3; ++k) { r->world_min[k] = fs.world_min[k]; r->world_max[k] = fs.world_max[k]; }
 		r->staged_uid = s->uid; r->staged_version = s->version;
 	}
 	const int rc_up = upload_staged_scene(r);
@@ -164,6 +165,7 @@ int rtb_renderer_share_scene(rtb_renderer* r, const rtb_renderer* src) {
 		r->staging = src->staging;
 		for (int i = 0; i < 7; ++i) r->off[i] = src->off[i];
 		r->staged_sv = src->staged_sv; r->staged_uid = src->staged_uid; r->staged_version = src->staged_version;
+		for (int k = 0; k < 3; ++k) { r->world_min[k] = src->world_min[k]; r->world_max[k] = src->world_max[k]; }
 		r->scene_stats = src->scene_stats;
 	}
 	const int rc_up = upload_staged_scene(r);
@@ -212,8 +214,8 @@ int rtb_renderer_set_camera(rtb_renderer* r, const rtb_camera* cam) {
 static int ensure_framebuffer(rtb_renderer* r, uint32_t w, uint32_t h) {
 	if (r->width == w && r->height == h && r->d_accum) return RTB_OK;
 	CUDA_TRY(cudaStreamSynchronize(r->stream));
-	cudaFree(r->d_accum); cudaFree(r->d_accum2); cudaFree(r->d_out);
-	r->d_accum = r->d_accum2 = r->d_out = nullptr;
+	cudaFree(r->d_accum); cudaFree(r->d_accum2); cudaFree(r->d_out); cudaFree(r->d_rgb8);
+	r->d_accum = r->d_accum2 = r->d_out = nullptr; r->d_rgb8 = nullptr; r->sample_cursor = 0;
 	size_t bytes = (size_t)w * h * sizeof(float4);
 	CUDA_TRY(cudaMalloc(&r->d_accum, bytes));
 	CUDA_TRY(cudaMalloc(&r->d_accum2, bytes));
@@ -231,6 +233,9 @@ static int ensure_wave(rtb_renderer* r, size_t paths, uint32_t depth) {
 	CUDA_TRY(cudaStreamSynchronize(r->stream));
 	free_graph(r);
 	cudaFree(r->d_wave); r->d_wave = nullptr;
+	if (paths < r->wave_paths) paths = r->wave_paths;     // grow-only in both dimensions: alternating sizes do not thrash
+	if (depth < r->wave_depth) depth = r->wave_depth;
+	r->wave_paths = 0; r->wave_depth = 0;
 	size_t P = align_up(paths, 256);
 	size_t off = 0;
 	auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -252,6 +257,8 @@ static int ensure_wave(rtb_renderer* r, size_t paths, uint32_t depth) {
 	return RTB_OK;
 }
 
+#define RTB_WAVE_BYTES_PER_PATH 152ull   // 6 x 16 (rays, throughput, double buffered) + 8 (hit) + 16 (contribution) + 32 (texture work list)
+
 // Bounces before which the fused tail kernel checks whether the live queue has become short.
 static bool tail_checkpoint(uint32_t b) {
 	static const uint32_t pts[] = {2, 3, 4, 5, 6, 8, 10, 12, 15, 18, 22, 27, 33, 40, 48, 58, 70, 85, 100};
@@ -262,7 +269,11 @@ static uint32_t count_tail_checkpoints(uint32_t depth) { uint32_t c = 0; for (ui
 
 static void enqueue_batch(rtb_renderer* r, const BatchParams& bp, cudaStream_t st) {
 	prof_begin(r, 0, st); launch_generate(bp, r->cam, r->wv, r->lc, st); prof_end(r, st);
+	// EXPERIMENT (profiling renders only, rtb_sort.cu): RTB_SORT_EXPERIMENT=<mode>[,<first bounce>,<last bounce>]
+	int sort_mode = 0; unsigned long long sort_mask = 0x1FEull;   // which bounces' queues are sorted before they are traversed (bit b)
+	if (r->profiling) if (const char* e = getenv("RTB_SORT_EXPERIMENT")) { unsigned m = 0; unsigned long long k2 = 0; int k = sscanf(e, "%u,%llx", &m, &k2); if (k >= 1) sort_mode = (int)m; if (k >= 2) sort_mask = k2; }
 	for (uint32_t b = 0; b < bp.max_depth; ++b) {
+		if (sort_mode && b < 64 && ((sort_mask >> b) & 1ull)) experimental_sort_queue(r, b, sort_mode, r->world_min, r->world_max);
 		if (r->tail_threshold && tail_checkpoint(b)) { prof_begin(r, 4, st); launch_tail(r->sv, bp, r->wv, b, r->tail_threshold, r->lc, st); prof_end(r, st); }
 		prof_begin(r, 1, st); launch_traverse(r->sv, bp, r->wv, b, r->lc, st); prof_end(r, st);
 		prof_begin(r, 2, st); launch_shade(r->sv, bp, r->wv, b, r->lc, st);
@@ -290,6 +301,15 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 	const uint64_t npix = (uint64_t)p->width * (row_end - row_begin);
 	uint64_t target_paths = 64ull << 20;   // ~9.7 GB of queues; larger batches keep late, thin bounces full (RTB_BATCH_PATHS overrides)
 	if (const char* e = getenv("RTB_BATCH_PATHS")) { uint64_t v = strtoull(e, nullptr, 10); if (v > 0) target_paths = v; }
+	if (!p->samples_per_batch && target_paths > r->wave_paths) {
+		// the queues cost RTB_WAVE_BYTES_PER_PATH per path: an automatic batch never asks for more than half of what is free
+		// (a smaller device, several renderers per device, a large scene) - it gets smaller instead of failing
+		size_t free_b = 0, total_b = 0;
+		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+			const uint64_t cap = (uint64_t)(free_b / 2 + r->wave_paths * RTB_WAVE_BYTES_PER_PATH) / RTB_WAVE_BYTES_PER_PATH;
+			if (target_paths > cap) target_paths = cap > npix ? cap : npix;
+		} else cudaGetLastError();
+	}
 	uint64_t S = p->samples_per_batch ? p->samples_per_batch : target_paths / npix;
 	if (S < 1) S = 1;
 	if (S > spp) S = spp ? spp : 1;
@@ -346,6 +366,7 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 	r->batches += n_batches;
 	CUDA_TRY(cudaEventRecord(r->ev_t1, st));
 	r->timed = true;
+	if ((p->flags & RTB_RENDER_CLEAR) || p->sample_end > r->sample_cursor) r->sample_cursor = p->sample_end;
 	// ... and let the caller's stream see the result
 	CUDA_TRY(cudaEventRecord(r->ev_out, st));
 	CUDA_TRY(cudaStreamWaitEvent(us, r->ev_out, 0));
@@ -364,16 +385,45 @@ void* rtb_renderer_accum2_ptr(rtb_renderer* r) { return r ? r->d_accum2 : nullpt
 
 int rtb_resolve(rtb_renderer* r, void* d_out, void* user_stream) {
 	if (!r || !r->d_accum) return fail(RTB_ERR_STATE, "rtb_resolve: nothing rendered");
+	return rtb_resolve_from(r, r->d_accum, d_out, user_stream);
+}
+
+}  // extern "C"
+
+int rtb_resolve_from(rtb_renderer* r, const float4* accum, void* d_out, void* user_stream) {
 	CUDA_TRY(cudaSetDevice(r->device));
 	cudaStream_t us = static_cast<cudaStream_t>(user_stream);
 	CUDA_TRY(cudaEventRecord(r->ev_in, us));
 	CUDA_TRY(cudaStreamWaitEvent(r->stream, r->ev_in, 0));
-	launch_resolve(r->d_accum, d_out ? static_cast<float4*>(d_out) : r->d_out, r->width * r->height, r->stream);
+	launch_resolve(accum, d_out ? static_cast<float4*>(d_out) : r->d_out, r->width * r->height, r->stream);
 	r->launches += 1;
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaEventRecord(r->ev_out, r->stream));
 	CUDA_TRY(cudaStreamWaitEvent(us, r->ev_out, 0));
 	return RTB_OK;
+}
+
+// 8-bit image the way write_renderbuffer makes it (FirstApp.cpp:108-122): uint8 = value * 255.999f of the resolved
+// image, RGB only, rows flipped when asked (row 0 of the float buffer is the bottom of the picture) - quantised on the
+// device, so the copy to the host is 3 bytes per pixel instead of 16.
+int rtb_quantize_from(rtb_renderer* r, const float4* accum, uint8_t* host_rgb, int flip_rows) {
+	CUDA_TRY(cudaSetDevice(r->device));
+	const size_t n = (size_t)r->width * r->height;
+	if (!r->d_rgb8) CUDA_TRY(cudaMalloc(&r->d_rgb8, n * 3));
+	launch_quantize(accum, r->d_rgb8, r->width, r->height, flip_rows, r->stream);
+	r->launches += 1;
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaMemcpyAsync(host_rgb, r->d_rgb8, n * 3, cudaMemcpyDeviceToHost, r->stream));
+	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	return RTB_OK;
+}
+
+extern "C" {
+
+int rtb_download_rgb8(rtb_renderer* r, uint8_t* host_rgb, int flip_rows) {
+	if (!r || !host_rgb) return fail(RTB_ERR_INVALID, "rtb_download_rgb8: null argument");
+	if (!r->d_accum) return fail(RTB_ERR_STATE, "rtb_download_rgb8: nothing rendered");
+	return rtb_quantize_from(r, r->d_accum, host_rgb, flip_rows);
 }
 
 int rtb_download(rtb_renderer* r, float* host_rgba) {
@@ -394,6 +444,53 @@ int rtb_download_accum(rtb_renderer* r, float* host_sum, float* host_sum2) {
 	CUDA_TRY(cudaStreamSynchronize(r->stream));
 	return RTB_OK;
 }
+
+// Checkpoint of a progressive render: the radiance sums, the sums of squares and the sample cursor.
+//   header: "RTBA", version 1, width, height, sample_cursor, reserved[3] (8 x uint32), then 2 x width*height float4.
+struct AccumFileHeader { uint32_t magic, version, width, height, sample_cursor, reserved[3]; };
+static const uint32_t ACCUM_MAGIC = 0x41425452u;   // "RTBA"
+
+int rtb_save_accum(rtb_renderer* r, const char* path) {
+	if (!r || !path) return fail(RTB_ERR_INVALID, "rtb_save_accum: null argument");
+	if (!r->d_accum) return fail(RTB_ERR_STATE, "rtb_save_accum: nothing rendered");
+	const size_t n = (size_t)r->width * r->height;
+	std::vector<float> sum(4 * n), sum2(4 * n);
+	int rc = rtb_download_accum(r, sum.data(), sum2.data());
+	if (rc) return rc;
+	FILE* f = fopen(path, "wb");
+	if (!f) return fail(RTB_ERR_INVALID, std::string("rtb_save_accum: cannot open ") + path);
+	AccumFileHeader h{ACCUM_MAGIC, 1u, r->width, r->height, r->sample_cursor, {0, 0, 0}};
+	bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(sum.data(), 16, n, f) == n && fwrite(sum2.data(), 16, n, f) == n;
+	ok = (fclose(f) == 0) && ok;
+	return ok ? RTB_OK : fail(RTB_ERR_INVALID, std::string("rtb_save_accum: short write to ") + path);
+}
+
+int rtb_load_accum(rtb_renderer* r, const char* path, uint32_t* width_out, uint32_t* height_out, uint32_t* sample_cursor_out) {
+	if (!r || !path) return fail(RTB_ERR_INVALID, "rtb_load_accum: null argument");
+	FILE* f = fopen(path, "rb");
+	if (!f) return fail(RTB_ERR_INVALID, std::string("rtb_load_accum: cannot open ") + path);
+	AccumFileHeader h{};
+	if (fread(&h, sizeof h, 1, f) != 1 || h.magic != ACCUM_MAGIC || h.version != 1u || h.width == 0 || h.height == 0 ||
+	    (uint64_t)h.width * h.height >= (1ull << 31)) { fclose(f); return fail(RTB_ERR_INVALID, std::string("rtb_load_accum: not an accumulator checkpoint: ") + path); }
+	const size_t n = (size_t)h.width * h.height;
+	std::vector<float> sum(4 * n), sum2(4 * n);
+	const bool ok = fread(sum.data(), 16, n, f) == n && fread(sum2.data(), 16, n, f) == n;
+	fclose(f);
+	if (!ok) return fail(RTB_ERR_INVALID, std::string("rtb_load_accum: truncated file ") + path);
+	CUDA_TRY(cudaSetDevice(r->device));
+	int rc = ensure_framebuffer(r, h.width, h.height);
+	if (rc) return rc;
+	CUDA_TRY(cudaMemcpyAsync(r->d_accum, sum.data(), 16 * n, cudaMemcpyHostToDevice, r->stream));
+	CUDA_TRY(cudaMemcpyAsync(r->d_accum2, sum2.data(), 16 * n, cudaMemcpyHostToDevice, r->stream));
+	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	r->sample_cursor = h.sample_cursor;
+	if (width_out) *width_out = h.width;
+	if (height_out) *height_out = h.height;
+	if (sample_cursor_out) *sample_cursor_out = h.sample_cursor;
+	return RTB_OK;
+}
+
+uint32_t rtb_renderer_sample_cursor(const rtb_renderer* r) { return r ? r->sample_cursor : 0; }
 
 int rtb_get_counters(rtb_renderer* r, rtb_counters* out) {
 	if (!r || !out) return fail(RTB_ERR_INVALID, "rtb_get_counters: null argument");
@@ -437,6 +534,18 @@ int rtb_get_profile(rtb_renderer* r, rtb_profile* out) {
 	return RTB_OK;
 }
 
+int rtb_get_profile_launches(rtb_renderer* r, float* ms_out, int32_t* class_out, int cap) {
+	if (!r || cap < 0 || (cap && (!ms_out || !class_out))) return fail(RTB_ERR_INVALID, "rtb_get_profile_launches: bad argument");
+	CUDA_TRY(cudaSetDevice(r->device));
+	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	for (size_t i = 0; i < r->prof_used && (int)i < cap; ++i) {
+		float t = 0.0f;
+		CUDA_TRY(cudaEventElapsedTime(&t, r->prof_events[2 * i], r->prof_events[2 * i + 1]));
+		ms_out[i] = t; class_out[i] = r->prof_class[i];
+	}
+	return (int)r->prof_used;
+}
+
 int rtb_queue_lengths(rtb_renderer* r, uint32_t* out, int cap) {
 	if (!r || !out || cap <= 0) return fail(RTB_ERR_INVALID, "rtb_queue_lengths: bad argument");
 	if (!r->d_wave) return fail(RTB_ERR_STATE, "rtb_queue_lengths: nothing rendered");
@@ -461,6 +570,10 @@ int rtb_trace_rays(rtb_renderer* r, const rtb_ray* rays, size_t n, rtb_hit* hits
 	if (!r->has_scene) return fail(RTB_ERR_STATE, "rtb_trace_rays: no scene");
 	if (n == 0) return RTB_OK;
 	if (n >= (1ull << 31)) return fail(RTB_ERR_INVALID, "rtb_trace_rays: too many rays");
+	if (r->sv.bvh_empty) {   // nothing but pre-listed media (which this hook skips): every ray misses, and there is no node 0 to start from
+		for (size_t i = 0; i < n; ++i) { rtb_hit h{}; h.t = 3.402823466e+38f; h.prim = h.object = h.material = -1; hits_out[i] = h; }
+		return RTB_OK;
+	}
 	CUDA_TRY(cudaSetDevice(r->device));
 	std::vector<float4> ho(n), hd(n);
 	for (size_t i = 0; i < n; ++i) {

@@ -37,12 +37,15 @@ struct rtb_renderer {
 	rtb_scene_stats scene_stats{};
 	GpuScratch build_scratch;   // grow-only scratch of the GPU BVH build
 	uint64_t scene_version = 0;
+	float world_min[3] = {0, 0, 0}, world_max[3] = {0, 0, 0};   // bounds of the world BVH
 	rtb_camera cam{};
 	bool has_cam = false;
 
 	// framebuffers
 	uint32_t width = 0, height = 0;
 	float4 *d_accum = nullptr, *d_accum2 = nullptr, *d_out = nullptr;
+	uint8_t* d_rgb8 = nullptr;              // 8-bit output (rtb_download_rgb8)
+	uint32_t sample_cursor = 0;             // one past the last sample index accumulated since the last clear (checkpoints)
 
 	// wavefront queues
 	void* d_wave = nullptr; size_t wave_paths = 0; uint32_t wave_depth = 0;
@@ -68,5 +71,7 @@ struct rtb_renderer {
 // Resolve (mean -> clamp -> sqrt) of an arbitrary accumulator on this renderer's device and stream (rtb_multi.cu resolves
 // the cross-device total with it).
 int rtb_resolve_from(rtb_renderer* r, const float4* accum, void* d_out, void* user_stream);
+namespace rtb { int experimental_sort_queue(rtb_renderer* r, uint32_t bounce, int mode, const float* world_min, const float* world_max); }   // rtb_sort.cu
+int rtb_quantize_from(rtb_renderer* r, const float4* accum, uint8_t* host_rgb, int flip_rows);
 
 #endif

@@ -1015,6 +1015,7 @@ int flatten(rtb_scene& s, FlatScene& out, const GpuBuildContext* gpu) {
 		});
 		out.root_ref = 0;
 	}
+	for (int k = 0; k < 3; ++k) { out.world_min[k] = nodes[root_idx].bmin[k]; out.world_max[k] = nodes[root_idx].bmax[k]; }
 	s.world_nodes = std::move(nodes); s.world_root = root_idx;
 
 	}

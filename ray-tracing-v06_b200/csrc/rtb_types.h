@@ -79,6 +79,7 @@ struct FlatScene {
 	int32_t max_depth_nodes = 0;         // tree depth (stack bound check)
 	int32_t builder = 0;                 // rtb_world_bvh_mode that produced the tree (3 = median fallback)
 	int32_t n_items = 0;                 // BVH leaves
+	float world_min[3] = {0, 0, 0}, world_max[3] = {0, 0, 0};   // bounds of the world BVH
 	float flatten_ms = 0.0f, bvh_build_ms = 0.0f;
 };
 
