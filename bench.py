@@ -258,7 +258,7 @@ def main():
         s0p = ((args.warmup + args.steps + e2e_steps) * world + rank) * S
         r.render(W, H, s0p, s0p + S, depth, seed=1984, clear=True, stream=stream)   # rank-local: no collective here
         prof = r.profile(); pc = r.counters(); r.set_profiling(False)
-        total_ms = prof.generate_ms + prof.traverse_ms + prof.shade_ms + prof.accumulate_ms + prof.tail_ms
+        total_ms = prof.generate_ms + prof.traverse_ms + prof.shade_ms + prof.accumulate_ms + prof.tail_ms + prof.bin_ms
         ach = ALG_BYTES_PER_RAY_TRAVERSE * pc.rays / (prof.traverse_ms * 1e-3) / 1e9 if prof.traverse_ms > 0 else 0.0
         traffic = None
         try:   # DRAM bytes per ray of the kernel from the committed ncu --set full capture, scaled to this run's rays per launch
@@ -296,7 +296,7 @@ def main():
         except Exception as e:   # the counters are diagnostics: never fail the bench line over them
             roof["fp32"] = {"error": str(e)}
         step_bytes = ALG_BYTES_PER_RAY_STEP * rays + ALG_BYTES_PER_PATH_STEP * paths
-        split = {"traverse_ms": prof.traverse_ms, "shade_ms": prof.shade_ms, "generate_ms": prof.generate_ms, "accumulate_ms": prof.accumulate_ms, "tail_ms": prof.tail_ms,
+        split = {"traverse_ms": prof.traverse_ms, "shade_ms": prof.shade_ms, "generate_ms": prof.generate_ms, "accumulate_ms": prof.accumulate_ms, "tail_ms": prof.tail_ms, "bin_ms": prof.bin_ms,
                  "traverse_share": prof.traverse_ms / total_ms if total_ms else None,
                  "step_hbm_frac_152B_per_ray": step_bytes / (ms * 1e-3) / 1e9 / peak / max(1, world)}
 

@@ -266,11 +266,14 @@ typedef struct rtb_profile {
 	uint64_t generate_launches, traverse_launches, shade_launches, accumulate_launches;
 	double   tail_ms;          /* fused traverse+shade kernel that finishes short queues */
 	uint64_t tail_launches;
+	double   bin_ms;           /* ray binning between bounces (bin_scan + bin_permute) */
+	uint64_t bin_launches;
 } rtb_profile;
 int  rtb_renderer_set_profiling(rtb_renderer* r, int on);
 int  rtb_get_profile(rtb_renderer* r, rtb_profile* out);   /* synchronizes; totals since the last call */
 /* The individual launches behind rtb_get_profile, in launch order (call it BEFORE rtb_get_profile, which resets):
- * ms_out[i] = device time, class_out[i] = 0 generate, 1 traverse, 2 shade (+ texture), 3 accumulate, 4 tail check.
+ * ms_out[i] = device time, class_out[i] = 0 generate, 1 traverse, 2 shade (+ texture), 3 accumulate, 4 tail check,
+ * 5 ray binning.
  * Returns the number of launches recorded (may exceed cap). */
 int  rtb_get_profile_launches(rtb_renderer* r, float* ms_out, int32_t* class_out, int cap);
 int  rtb_reset_counters(rtb_renderer* r);
@@ -298,6 +301,13 @@ typedef struct rtb_hit {                                                        
 /* Closest hits for n host rays through the traversal code of the wavefront (media are skipped: they are
  * stochastic), with the full hit record materials would see and per-ray traversal statistics. */
 int rtb_trace_rays(rtb_renderer* r, const rtb_ray* rays, size_t n, rtb_hit* hits_out);
+
+/* Memory-safety evidence without compute-sanitizer: librtb200_debug.so is this library built with -DRTB_DEBUG_BOUNDS=1,
+ * in which every index the kernels form from scene or queue data (traversal stack slot, node, primitive record, material,
+ * texture / texel, queue slot, path id, bin) is checked against the size of what it indexes; violations are counted per
+ * class - violations_out[0..7] in that order - instead of trapping, checks_out counts the rays that went through checked
+ * kernels.  Returns the number of classes, or RTB_ERR_UNSUPPORTED from the release library. */
+int rtb_debug_bounds_report(rtb_renderer* r, uint64_t* violations_out, int cap, uint64_t* checks_out);
 
 /* ------------------------------------------------------------------ several GPUs of one box
  *

@@ -21,6 +21,8 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ["RTB_LIB"]) if os.environ.get("RTB_LIB") else _HERE / "librtb200.so"   # RTB_LIB: experimental builds only
 SCENES_LIB_PATH = _HERE / "librtb200_scenes.so"
+DEBUG_LIB_PATH = _HERE / "librtb200_debug.so"     # the same library built with -DRTB_DEBUG_BOUNDS=1 (select it with RTB_LIB)
+BOUNDS_CLASSES = ("stack", "node", "primitive", "material", "texture", "queue", "path", "bin")
 
 RTB_OK = 0
 TEX_SOLID, TEX_CHECKER, TEX_IMAGE, TEX_NOISE = 0, 1, 2, 3
@@ -31,7 +33,7 @@ BUILDER_NAMES = {0: "host_sah", 1: "as_built", 2: "gpu_lbvh", 3: "host_median_fa
 CAM_PINHOLE, CAM_DEFOCUS, CAM_MOTION = 0, 1, 2
 RENDER_CLEAR, RENDER_VARIANCE = 1, 2
 REDUCE_AUTO, REDUCE_NCCL, REDUCE_P2P = 0, 1, 2
-PROFILE_CLASSES = {0: "generate", 1: "traverse", 2: "shade", 3: "accumulate", 4: "tail"}
+PROFILE_CLASSES = {0: "generate", 1: "traverse", 2: "shade", 3: "accumulate", 4: "tail", 5: "bin"}
 MISS_DIST = np.float32(3.402823466e38)
 
 
@@ -73,7 +75,7 @@ class SceneStats(C.Structure):
 class Profile(C.Structure):
     _fields_ = [("generate_ms", C.c_double), ("traverse_ms", C.c_double), ("shade_ms", C.c_double), ("accumulate_ms", C.c_double),
                 ("generate_launches", C.c_uint64), ("traverse_launches", C.c_uint64), ("shade_launches", C.c_uint64), ("accumulate_launches", C.c_uint64),
-                ("tail_ms", C.c_double), ("tail_launches", C.c_uint64)]
+                ("tail_ms", C.c_double), ("tail_launches", C.c_uint64), ("bin_ms", C.c_double), ("bin_launches", C.c_uint64)]
 
 
 class SceneInfo(C.Structure):
@@ -155,6 +157,7 @@ ABI = {
     "rtb_load_accum": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "rtb_renderer_sample_cursor": (C.c_uint32, [_P]),
     "rtb_get_profile_launches": (C.c_int, [_P, _P, _P, C.c_int]),
+    "rtb_debug_bounds_report": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_uint64)]),
     "rtb_multi_renderer_create": (C.c_int, [C.POINTER(_P), C.POINTER(C.c_int), C.c_int, C.c_int]),
     "rtb_multi_renderer_destroy": (None, [_P]),
     "rtb_multi_device_count": (C.c_int, [_P]),
@@ -475,6 +478,14 @@ class Renderer:
         n = _check(lib().rtb_get_profile_launches(self.handle, ms.ctypes.data, cls.ctypes.data, cap), "rtb_get_profile_launches")
         n = min(n, cap)
         return ms[:n].copy(), cls[:n].copy()
+
+    def debug_bounds_report(self) -> dict:
+        """Out-of-range indices counted by the kernels of the debug build (RTB_LIB=librtb200_debug.so); raises with the release library."""
+        v = (C.c_uint64 * 8)(); checks = C.c_uint64(0)
+        _check(lib().rtb_debug_bounds_report(self.handle, v, 8, C.byref(checks)), "rtb_debug_bounds_report")
+        out = {name: int(v[i]) for i, name in enumerate(BOUNDS_CLASSES)}
+        out["rays_checked"] = int(checks.value)
+        return out
 
     def accum_tensor(self):
         """The device accumulator as a torch tensor (H, W, 4) sharing memory — used for the NCCL reduce."""

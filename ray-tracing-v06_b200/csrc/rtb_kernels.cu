@@ -34,6 +34,24 @@ using rt::v3;
 #define FULL_MASK 0xFFFFFFFFu
 
 // ------------------------------------------------------------------------------------------------
+// -DRTB_DEBUG_BOUNDS=1 (librtb200_debug.so): every index the kernels form from scene or queue data is checked against
+// the size of what it indexes, and violations are counted per class instead of trapping (compute-sanitizer is not
+// available on the pool this was developed on).  rtb_debug_bounds_report returns the counters; the release build
+// compiles the checks away.
+#ifndef RTB_DEBUG_BOUNDS
+#define RTB_DEBUG_BOUNDS 0
+#endif
+#if RTB_DEBUG_BOUNDS
+__device__ unsigned long long g_bounds_violations[RTB_BOUNDS_CLASSES];
+__device__ unsigned long long g_bounds_checks;
+#define RTB_CHECK(ok, cls) do { if (!(ok)) atomicAdd(&g_bounds_violations[cls], 1ull); } while (0)
+#define RTB_COUNT_CHECKS(n) atomicAdd(&g_bounds_checks, (unsigned long long)(n))
+#else
+#define RTB_CHECK(ok, cls) do { } while (0)
+#define RTB_COUNT_CHECKS(n) do { } while (0)
+#endif
+
+// ------------------------------------------------------------------------------------------------
 // small device helpers
 
 __device__ __forceinline__ v3 xyz(const float4& f) { return rt::mk(f.x, f.y, f.z); }
@@ -336,6 +354,7 @@ __device__ __forceinline__ float leaf_test(const SceneView& sv, int code, v3 o, 
                                            const RaySlab& rs, int& hit_code) {
 	hit_code = code;
 	const int type = code & 15;
+	RTB_CHECK(code >= 0 && (code >> RTB_LEAF_TYPE_BITS) < sv.n_prims, RTB_BOUNDS_PRIM);
 	const float4* pp = sv.prims + 4 * (size_t)(code >> RTB_LEAF_TYPE_BITS);
 	const float4 q0 = ldg4(pp);
 	float t = FLT_MAX;
@@ -428,7 +447,7 @@ __device__ __forceinline__ float leaf_test(const SceneView& sv, int code, v3 o, 
 // one: no RNG state is carried through the loop); 2 = more than the list holds, the rest are BVH leaves.
 template <int MEDIA, bool STATS = false>
 __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float time, MediumRng& mr,
-                                          int* __restrict__ stack, float& tbest_out, int& code_out, int* stats_out = nullptr) {
+                                          int* __restrict__ stack, int stack_cap, float& tbest_out, int& code_out, int* stats_out = nullptr) {
 	const float a = rt::dot(d, d);
 	float tbest = FLT_MAX;
 	int best = -1;
@@ -473,6 +492,7 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 	for (;;) {
 		while (cur >= 0) {
 			if (STATS) ++n_inner;
+			RTB_CHECK(cur < sv.n_nodes, RTB_BOUNDS_NODE);
 			const float4* np = sv.nodes + 4 * (size_t)cur;
 			float4 n0, n1, n2, n3f;
 			ldg8(np, n0, n1); ldg8(np + 2, n2, n3f);
@@ -517,6 +537,7 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 				// the origin are ordered by where the ray leaves them
 				const float lk = fmaxf(ltmin, 0.0f), rk = fmaxf(rtmin, 0.0f);
 				const bool sw = lk > rk || (lk == rk && ltmax > rtmax);
+				RTB_CHECK(sp >= 0 && sp < stack_cap, RTB_BOUNDS_STACK);
 				stack[sp * TRAVERSE_THREADS] = sw ? n3.x : n3.y; ++sp;
 				cur = sw ? n3.y : n3.x;
 			} else if (hl) cur = n3.x;
@@ -550,15 +571,16 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 // block instead of 16 KB leaves 64 KB more L1 per SM: -2 % on the Book 2 final scene), 32 otherwise.
 template <int MEDIA, int STACK>
 __global__ void __launch_bounds__(TRAVERSE_THREADS, TRAVERSE_MIN_BLOCKS)
-traverse_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
+traverse_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce, int q) {
 	__shared__ int s_stack[STACK * TRAVERSE_THREADS];
 	if (bounce >= *wv.tail_from) return;
 	const uint32_t n = wv.n_live[bounce];
 	if (n == 0) return;
+	if (blockIdx.x == 0 && threadIdx.x == 0) { RTB_COUNT_CHECKS(n); RTB_CHECK(n <= wv.capacity, RTB_BOUNDS_QUEUE); }
 	const uint32_t batch = *wv.batch_index;
 	const int lane = threadIdx.x & 31;
-	const float4* __restrict__ ro = (bounce & 1) ? wv.ray_o[1] : wv.ray_o[0];
-	const float4* __restrict__ rd = (bounce & 1) ? wv.ray_d[1] : wv.ray_d[0];
+	const float4* __restrict__ ro = q ? wv.ray_o[1] : wv.ray_o[0];
+	const float4* __restrict__ rd = q ? wv.ray_d[1] : wv.ray_d[0];
 	uint32_t* counter = wv.work + 2 * bounce;
 	// Every warp owns one static chunk of 32 rays; only when the queue is longer than the whole
 	// grid do warps pull further chunks from the device counter (short queues cost no atomics).
@@ -571,7 +593,8 @@ traverse_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
 			const float4 fo = ldq(ro + i), fd = ldq(rd + i);
 			MediumRng mr = make_medium_rng(bp, batch, __float_as_uint(fd.w), bounce);
 			float t; int code;
-			trace_ray<MEDIA>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code);
+			trace_ray<MEDIA>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, STACK, t, code);
+			RTB_CHECK(i < wv.capacity, RTB_BOUNDS_QUEUE);
 			stq(wv.hit + i, make_int2(__float_as_int(t), code));
 		}
 		__syncwarp();
@@ -592,6 +615,7 @@ struct Surface { v3 p, n_shade, n_geom; float u, v; };
 __device__ __forceinline__ void reconstruct(const SceneView& sv, int code, v3 o, v3 d, float time, float t, bool want_uv, Surface& s) {
 	const int type = code & 15, base = type & 7;
 	const bool xf = (type & PRIM_XF) != 0;
+	RTB_CHECK(code >= 0 && (code >> RTB_LEAF_TYPE_BITS) + (xf && base >= PRIM_QUAD ? 1 : 0) < sv.n_prims, RTB_BOUNDS_PRIM);
 	const float4* pp = sv.prims + 4 * (size_t)(code >> RTB_LEAF_TYPE_BITS);
 	const float4 q0 = ldg4(pp);
 	s.p = rt::madd(d, t, o);          // Material::Scatter uses in_ray.at(rec.distance): the world ray
@@ -661,6 +685,7 @@ __device__ float perlin_noise(const float* __restrict__ grad, const int* __restr
 
 __device__ v3 texture_value(const SceneView& sv, int tex, float u, float v, v3 p) {
 	for (int guard = 0; guard < 16; ++guard) {
+		RTB_CHECK(tex >= 0 && tex < sv.n_textures, RTB_BOUNDS_TEXTURE);
 		const float4 t0 = ldg4(sv.textures + 3 * tex);
 		const int kind = __float_as_int(t0.x);
 		if (kind == RTB_TEX_SOLID) { return xyz(ldg4(sv.textures + 3 * tex + 1)); }
@@ -678,6 +703,7 @@ __device__ v3 texture_value(const SceneView& sv, int tex, float u, float v, v3 p
 			float uc = fminf(fmaxf(u, 0.0f), 1.0f), vc = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
 			int i = (int)(uc * (float)w), j = (int)(vc * (float)h);
 			i = i < w - 1 ? i : w - 1; j = j < h - 1 ? j : h - 1;
+			RTB_CHECK(i >= 0 && j >= 0 && off + 3 * ((size_t)j * w + i) + 2 < sv.n_blob, RTB_BOUNDS_TEXTURE);
 			const uint8_t* px = sv.blob + off + 3 * ((size_t)j * w + i);
 			const float sc = 1.0f / 255.0f;
 			return rt::mk(sc * (float)px[0], sc * (float)px[1], sc * (float)px[2]);
@@ -709,6 +735,7 @@ __device__ __forceinline__ bool texture_needs_uv(const SceneView& sv, int tex) {
 // left at 1 and defer_tex names the texture, to be multiplied in later by texture_kernel (dense warps).
 template <bool DEFER>
 __device__ __forceinline__ int scatter(const SceneView& sv, int mat, const Surface& s, v3 d, const rt::f4& r, v3& dir, v3& att, int& defer_tex) {
+	RTB_CHECK(mat >= 0 && mat < sv.n_materials, RTB_BOUNDS_MATERIAL);
 	const float4 m0 = ldg4(sv.materials + 2 * mat), m1 = ldg4(sv.materials + 2 * mat + 1);
 	const int kind = __float_as_int(m0.x), tex = __float_as_int(m0.y);
 	const float param = m0.z;
@@ -791,7 +818,10 @@ __device__ __forceinline__ bool shade_segment(const SceneView& sv, const BatchPa
 		wv.contrib[path] = make_float4(c.x, c.y, c.z, 0.0f);
 		return false;
 	}
+	RTB_CHECK((code >> RTB_LEAF_TYPE_BITS) < sv.n_prims, RTB_BOUNDS_PRIM);
 	const int2 info = __ldg(sv.prim_info + (code >> RTB_LEAF_TYPE_BITS));
+	RTB_CHECK(info.x >= 0 && info.x < sv.n_materials, RTB_BOUNDS_MATERIAL);
+	RTB_CHECK(path < wv.capacity, RTB_BOUNDS_PATH);
 	const int tex = __float_as_int(ldg4(sv.materials + 2 * info.x).y);
 	Surface s;
 	reconstruct(sv, code, o, d, fo.w, t, texture_needs_uv(sv, tex), s);
@@ -815,15 +845,50 @@ __device__ __forceinline__ bool shade_segment(const SceneView& sv, const BatchPa
 	return true;
 }
 
+// Bin of a ray for the binning pass: Morton code of the origin's cell on a 2^org_bits cube over the world bounds, then the
+// cell of the direction on a 2^dir_bits square of the octahedral map.  Rays of one bin start close together and head the
+// same way, so the lanes of a warp walk the same nodes (measured on B200: 12 -> 20+ active lanes on secondary bounces).
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {   // 10 bits -> every third bit
+	v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u;
+	return v;
+}
+__device__ __forceinline__ uint32_t ray_bin(const SceneView& sv, const float4& o, const float4& d) {
+	const int qo = 1 << sv.bin_org_bits;
+	int ix = (int)((o.x - sv.bin_min[0]) * sv.bin_scale[0]), iy = (int)((o.y - sv.bin_min[1]) * sv.bin_scale[1]), iz = (int)((o.z - sv.bin_min[2]) * sv.bin_scale[2]);
+	ix = min(max(ix, 0), qo - 1); iy = min(max(iy, 0), qo - 1); iz = min(max(iz, 0), qo - 1);
+	uint32_t key = spread3((uint32_t)ix) | (spread3((uint32_t)iy) << 1) | (spread3((uint32_t)iz) << 2);
+	if (sv.bin_dir_bits > 0) {
+		const float s = 1.0f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z) + 1e-30f);
+		float u = d.x * s, v = d.z * s;
+		if (d.y < 0.0f) { const float uu = (1.0f - fabsf(v)) * (u >= 0.0f ? 1.0f : -1.0f), vv = (1.0f - fabsf(u)) * (v >= 0.0f ? 1.0f : -1.0f); u = uu; v = vv; }
+		const int qd = 1 << sv.bin_dir_bits;
+		int iu = (int)((u * 0.5f + 0.5f) * (float)qd), iv = (int)((v * 0.5f + 0.5f) * (float)qd);
+		iu = min(max(iu, 0), qd - 1); iv = min(max(iv, 0), qd - 1);
+		key = (key << (2 * sv.bin_dir_bits)) | (uint32_t)(iv * qd + iu);
+	}
+	return key;
+}
+// One atomic per distinct bin among the active lanes of a warp; returns this lane's slot (base of its bin's run + rank).
+__device__ __forceinline__ uint32_t warp_bin_add(uint32_t* counters, uint32_t counters_size, uint32_t bin) {
+	RTB_CHECK(bin < counters_size, RTB_BOUNDS_BIN);
+	const uint32_t act = __activemask();
+	const uint32_t peers = __match_any_sync(act, bin);
+	const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+	uint32_t base = 0;
+	if (lane == leader) base = atomicAdd(counters + bin, (uint32_t)__popc(peers));
+	base = __shfl_sync(peers, base, leader);
+	return base + __popc(peers & ((1u << lane) - 1u));
+}
+
 __global__ void __launch_bounds__(SHADE_THREADS)
-shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
+shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce, int q, int count_bins) {
 	__shared__ uint32_t s_chunk, s_base;
 	__shared__ uint32_t s_warp[SHADE_THREADS / 32];
 	if (bounce >= *wv.tail_from) return;
 	const uint32_t n = wv.n_live[bounce];
 	if (n == 0) return;
 	const uint32_t batch = *wv.batch_index;
-	const int in = bounce & 1, out = in ^ 1;
+	const int in = q, out = in ^ 1;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const float4* __restrict__ ro = in ? wv.ray_o[1] : wv.ray_o[0];
 	const float4* __restrict__ rd = in ? wv.ray_d[1] : wv.ray_d[0];
@@ -860,7 +925,9 @@ shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
 		__syncthreads();
 		if (alive) {
 			const uint32_t pos = s_base + s_warp[warp] + __popc(mask & ((1u << lane) - 1u));
+			RTB_CHECK(pos < wv.capacity && pos < n, RTB_BOUNDS_QUEUE);
 			stq(wo + pos, no); stq(wd + pos, nd); stq(wt + pos, make_float4(nthr.x, nthr.y, nthr.z, 0.0f));
+			if (count_bins) warp_bin_add(wv.bin_count, wv.n_bins, ray_bin(sv, no, nd));
 			// texture work list: (p, queue slot), (u, v, -, texture id)
 			const bool defer = dt.tex >= 0;
 			const uint32_t act = __activemask();
@@ -887,19 +954,66 @@ shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce) {
 // into the throughput of the scattered rays (thr * value is the same single product either way).
 
 __global__ void __launch_bounds__(STREAM_THREADS)
-texture_kernel(SceneView sv, WaveView wv, uint32_t bounce) {
+texture_kernel(SceneView sv, WaveView wv, uint32_t bounce, int q_out) {
 	if (bounce >= *wv.tail_from) return;
 	const uint32_t n = wv.n_tex[bounce];
 	if (n == 0) return;
-	float4* __restrict__ wt = ((bounce & 1) ^ 1) ? wv.thr[1] : wv.thr[0];
+	float4* __restrict__ wt = q_out ? wv.thr[1] : wv.thr[0];
 	const uint32_t stride = gridDim.x * blockDim.x;
 	for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
 		const float4 a = wv.tex_work[2 * (size_t)k], b = wv.tex_work[2 * (size_t)k + 1];
 		const v3 val = texture_value(sv, __float_as_int(b.w), b.x, b.y, xyz(a));
 		const uint32_t pos = __float_as_uint(a.w);
+		RTB_CHECK(pos < wv.capacity && __float_as_int(b.w) >= 0 && __float_as_int(b.w) < sv.n_textures, RTB_BOUNDS_QUEUE);
 		float4 t = wt[pos];
 		t.x *= val.x; t.y *= val.y; t.z *= val.z;
 		wt[pos] = t;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// binning: shade counted the rays of the next bounce per bin; bin_scan turns the counts into the first slot of every bin
+// (and leaves the counters zero for their next use), bin_permute moves every ray to the next free slot of its bin in the
+// other queue.  Where a ray sits in a queue changes nothing about the image - contributions are stored by path id and
+// summed per pixel in sample order - only which rays share a warp.
+
+#define BIN_SCAN_THREADS 1024
+__global__ void __launch_bounds__(BIN_SCAN_THREADS)
+bin_scan_kernel(WaveView wv, uint32_t bounce, uint32_t nbins) {
+	__shared__ uint32_t s_part[BIN_SCAN_THREADS];
+	if (bounce >= *wv.tail_from || wv.n_live[bounce] == 0) return;   // (shade did not count either)
+	const uint32_t per = (nbins + BIN_SCAN_THREADS - 1) / BIN_SCAN_THREADS;
+	const uint32_t b0 = min(threadIdx.x * per, nbins), b1 = min(b0 + per, nbins);
+	uint32_t sum = 0;
+	for (uint32_t b = b0; b < b1; ++b) sum += wv.bin_count[b];
+	s_part[threadIdx.x] = sum;
+	__syncthreads();
+	for (uint32_t off = 1; off < BIN_SCAN_THREADS; off <<= 1) {        // inclusive scan of the per-thread sums
+		const uint32_t v = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0u;
+		__syncthreads();
+		s_part[threadIdx.x] += v;
+		__syncthreads();
+	}
+	uint32_t run = s_part[threadIdx.x] - sum;
+	for (uint32_t b = b0; b < b1; ++b) { const uint32_t c = wv.bin_count[b]; wv.bin_cursor[b] = run; wv.bin_count[b] = 0u; run += c; }
+}
+
+__global__ void __launch_bounds__(STREAM_THREADS)
+bin_permute_kernel(SceneView sv, WaveView wv, uint32_t bounce, int q_from) {
+	if (bounce >= *wv.tail_from) return;
+	const uint32_t n = wv.n_live[bounce];
+	const float4* __restrict__ ro = q_from ? wv.ray_o[1] : wv.ray_o[0];
+	const float4* __restrict__ rd = q_from ? wv.ray_d[1] : wv.ray_d[0];
+	const float4* __restrict__ rt_ = q_from ? wv.thr[1] : wv.thr[0];
+	float4* __restrict__ wo = q_from ? wv.ray_o[0] : wv.ray_o[1];
+	float4* __restrict__ wd = q_from ? wv.ray_d[0] : wv.ray_d[1];
+	float4* __restrict__ wt = q_from ? wv.thr[0] : wv.thr[1];
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const float4 o = ldq(ro + i), d = ldq(rd + i), t = ldq(rt_ + i);
+		const uint32_t pos = warp_bin_add(wv.bin_cursor, wv.n_bins, ray_bin(sv, o, d));
+		RTB_CHECK(pos < n && pos < wv.capacity, RTB_BOUNDS_QUEUE);
+		wo[pos] = o; wd[pos] = d; wt[pos] = t;
 	}
 }
 
@@ -910,14 +1024,14 @@ texture_kernel(SceneView sv, WaveView wv, uint32_t bounce) {
 
 template <bool MEDIA, int STACK>
 __global__ void __launch_bounds__(TRAVERSE_THREADS)
-tail_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce0, uint32_t threshold) {
+tail_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce0, int q, uint32_t threshold) {
 	__shared__ int s_stack[STACK * TRAVERSE_THREADS];
 	if (*wv.tail_from < bounce0) return;                 // an earlier checkpoint already took the batch over
 	const uint32_t n = wv.n_live[bounce0];
 	if (n == 0 || n > threshold) return;
 	if (blockIdx.x == 0 && threadIdx.x == 0) *wv.tail_from = bounce0;
 	const uint32_t batch = *wv.batch_index;
-	const int in = bounce0 & 1;
+	const int in = q;
 	const float4* __restrict__ ro = in ? wv.ray_o[1] : wv.ray_o[0];
 	const float4* __restrict__ rd = in ? wv.ray_d[1] : wv.ray_d[0];
 	const float4* __restrict__ rt_ = in ? wv.thr[1] : wv.thr[0];
@@ -931,7 +1045,7 @@ tail_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce0, uint32_
 			if (b > bounce0) ++extra;
 			mr.bounce = b; mr.block = 0xFFFFFFFFu;
 			float t; int code;
-			trace_ray<(MEDIA ? 2 : 0)>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code);
+			trace_ray<(MEDIA ? 2 : 0)>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, STACK, t, code);
 			float4 no, nd; v3 nthr;
 			DeferredTex dt;
 			if (!shade_segment<false>(sv, bp, wv, batch, b, fo, fd, thr, t, code, no, nd, nthr, dt)) break;
@@ -1026,7 +1140,7 @@ trace_rays_kernel(SceneView sv, const float4* __restrict__ ro, const float4* __r
 			MediumRng mr = make_medium_rng(BatchParams{}, 0, 0, 0);
 			float t; int code;
 			int st[2];
-			trace_ray<0, true>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, t, code, st);
+			trace_ray<0, true>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, STACK, t, code, st);
 			hit[i] = make_int2(__float_as_int(t), code);
 			stats[i] = make_int2(st[0], st[1]);
 		}
@@ -1064,6 +1178,17 @@ hit_record_kernel(SceneView sv, const float4* __restrict__ ro, const float4* __r
 // ------------------------------------------------------------------------------------------------
 // host launch wrappers
 
+int debug_bounds_report(unsigned long long* violations, unsigned long long* checks) {
+#if RTB_DEBUG_BOUNDS
+	if (cudaMemcpyFromSymbol(violations, g_bounds_violations, sizeof(unsigned long long) * RTB_BOUNDS_CLASSES) != cudaSuccess) return -1;
+	if (cudaMemcpyFromSymbol(checks, g_bounds_checks, sizeof(unsigned long long)) != cudaSuccess) return -1;
+	return 1;
+#else
+	(void)violations; (void)checks;
+	return 0;
+#endif
+}
+
 void query_occupancy(int device, LaunchCfg& lc) {
 	cudaDeviceProp prop{};
 	cudaGetDeviceProperties(&prop, device);
@@ -1088,36 +1213,41 @@ void query_occupancy(int device, LaunchCfg& lc) {
 void launch_generate(const BatchParams& bp, const rtb_camera& cam, const WaveView& wv, const LaunchCfg& lc, cudaStream_t st) {
 	generate_kernel<<<lc.blocks_stream, STREAM_THREADS, 0, st>>>(bp, cam, wv);
 }
-void launch_traverse(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st) {
+void launch_traverse(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, int q, const LaunchCfg& lc, cudaStream_t st) {
 	// media need the per-path RNG inside traversal; scenes without media skip that code entirely
 	// a walk keeps at most depth - 1 entries on its stack: 16 entries for shallow trees, 32 normally, 64 for the deep
 	// trees a linear BVH over a large mesh can be (the flattener never hands over more than RTB_TREE_DEPTH_MAX levels)
 	const bool small = sv.tree_depth <= 17, deep = sv.tree_depth > STACK_SIZE - 2;
 #define RTB_LAUNCH_TRAVERSE(M) \
-	do { if (small) traverse_kernel<M, 16><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce); \
-	     else if (deep) traverse_kernel<M, DEEP_STACK_SIZE><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce); \
-	     else traverse_kernel<M, STACK_SIZE><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce); } while (0)
+	do { if (small) traverse_kernel<M, 16><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, q); \
+	     else if (deep) traverse_kernel<M, DEEP_STACK_SIZE><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, q); \
+	     else traverse_kernel<M, STACK_SIZE><<<lc.blocks_traverse, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, q); } while (0)
 	if (sv.has_media == 0) RTB_LAUNCH_TRAVERSE(0);
 	else if (sv.has_media == 1) RTB_LAUNCH_TRAVERSE(1);
 	else RTB_LAUNCH_TRAVERSE(2);
 #undef RTB_LAUNCH_TRAVERSE
 }
-void launch_tail(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, uint32_t threshold, const LaunchCfg& lc, cudaStream_t st) {
+void launch_tail(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, int q, uint32_t threshold, const LaunchCfg& lc, cudaStream_t st) {
 	const bool deep = sv.tree_depth > STACK_SIZE - 2;
 	if (sv.has_media) {
-		if (deep) tail_kernel<true, DEEP_STACK_SIZE><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, threshold);
-		else tail_kernel<true, STACK_SIZE><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, threshold);
+		if (deep) tail_kernel<true, DEEP_STACK_SIZE><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, q, threshold);
+		else tail_kernel<true, STACK_SIZE><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, q, threshold);
 	} else {
-		if (deep) tail_kernel<false, DEEP_STACK_SIZE><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, threshold);
-		else tail_kernel<false, STACK_SIZE><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, threshold);
+		if (deep) tail_kernel<false, DEEP_STACK_SIZE><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, q, threshold);
+		else tail_kernel<false, STACK_SIZE><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, q, threshold);
 	}
 }
-void launch_shade(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st) {
-	shade_kernel<<<lc.blocks_shade, SHADE_THREADS, 0, st>>>(sv, bp, wv, bounce);
+void launch_shade(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, int q, int count_bins, const LaunchCfg& lc, cudaStream_t st) {
+	shade_kernel<<<lc.blocks_shade, SHADE_THREADS, 0, st>>>(sv, bp, wv, bounce, q, count_bins);
 }
-void launch_texture(const SceneView& sv, const WaveView& wv, uint32_t bounce, const LaunchCfg& lc, cudaStream_t st) {
+void launch_texture(const SceneView& sv, const WaveView& wv, uint32_t bounce, int q_out, const LaunchCfg& lc, cudaStream_t st) {
 	const int blocks = lc.sms * 2 < lc.blocks_stream ? lc.sms * 2 : lc.blocks_stream;   // short work lists: a small grid keeps the launch cheap
-	texture_kernel<<<blocks, STREAM_THREADS, 0, st>>>(sv, wv, bounce);
+	texture_kernel<<<blocks, STREAM_THREADS, 0, st>>>(sv, wv, bounce, q_out);
+}
+void launch_bin_rays(const SceneView& sv, const WaveView& wv, uint32_t bounce, int q_from, const LaunchCfg& lc, cudaStream_t st) {
+	const uint32_t nbins = 1u << (3 * sv.bin_org_bits + 2 * sv.bin_dir_bits);
+	bin_scan_kernel<<<1, BIN_SCAN_THREADS, 0, st>>>(wv, bounce, nbins);
+	bin_permute_kernel<<<lc.blocks_stream, STREAM_THREADS, 0, st>>>(sv, wv, bounce, q_from);
 }
 void launch_accumulate(const BatchParams& bp, const WaveView& wv, float4* accum, float4* accum2, const LaunchCfg& lc, cudaStream_t st) {
 	accumulate_kernel<<<lc.blocks_stream, STREAM_THREADS, 0, st>>>(bp, wv, accum, accum2);

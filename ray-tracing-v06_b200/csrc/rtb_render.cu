@@ -77,6 +77,8 @@ int rtb_renderer_create(rtb_renderer** out, int device) {
 	query_occupancy(device, r->lc);
 	r->tail_threshold = (uint32_t)r->lc.sms * 768u;   // ~6 warps of rays per SM sub-partition
 	if (const char* e = getenv("RTB_TAIL_THRESHOLD")) r->tail_threshold = (uint32_t)strtoul(e, nullptr, 10);
+	if (const char* e = getenv("RTB_BIN_BITS")) { int a = 0, b = 0; if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 0 && a <= 8 && b >= 0 && b <= 6 && 3 * a + 2 * b <= 26) { r->bin_org_bits = a; r->bin_dir_bits = b; } }
+	if (const char* e = getenv("RTB_BIN_MASK")) r->bin_mask = strtoull(e, nullptr, 16);
 	*out = r;
 	return RTB_OK;
 }
@@ -135,6 +137,8 @@ int rtb_renderer_set_scene(rtb_renderer* r, rtb_scene* s) {
 		r->staged_sv = SceneView{};
 		r->staged_sv.root_ref = fs.root_ref;
 		r->staged_sv.n_prims = (int32_t)fs.prims.size();
+		r->staged_sv.n_nodes = (int32_t)fs.nodes.size(); r->staged_sv.n_materials = (int32_t)fs.materials.size();
+		r->staged_sv.n_textures = (int32_t)fs.textures.size(); r->staged_sv.n_blob = (uint32_t)fs.blob.size();
 		r->staged_sv.tree_depth = fs.max_depth_nodes;
 		r->staged_sv.n_pre = (int32_t)fs.pre_list.size();
 		r->staged_sv.bvh_empty = fs.bvh_empty;
@@ -147,6 +151,12 @@ int rtb_renderer_set_scene(rtb_renderer* r, rtb_scene* s) {
 		r->staged_sv.background_mode = fs.background_mode;
 		r->staged_sv.bg_r = fs.background[0]; r->staged_sv.bg_g = fs.background[1]; r->staged_sv.bg_b = fs.background[2];
 		for (int k = 0; k < 3; ++k) { r->world_min[k] = fs.world_min[k]; r->world_max[k] = fs.world_max[k]; }
+		r->staged_sv.bin_org_bits = r->bin_org_bits; r->staged_sv.bin_dir_bits = r->bin_dir_bits;
+		for (int k = 0; k < 3; ++k) {
+			const float ext = fs.bin_max[k] - fs.bin_min[k];
+			r->staged_sv.bin_min[k] = fs.bin_min[k];
+			r->staged_sv.bin_scale[k] = ext > 0.0f ? (float)(1 << r->bin_org_bits) / ext : 0.0f;
+		}
 		r->staged_uid = s->uid; r->staged_version = s->version;
 	}
 	const int rc_up = upload_staged_scene(r);
@@ -165,6 +175,8 @@ int rtb_renderer_share_scene(rtb_renderer* r, const rtb_renderer* src) {
 		r->staging = src->staging;
 		for (int i = 0; i < 7; ++i) r->off[i] = src->off[i];
 		r->staged_sv = src->staged_sv; r->staged_uid = src->staged_uid; r->staged_version = src->staged_version;
+		for (int k = 0; k < 3; ++k) r->staged_sv.bin_scale[k] *= (float)(1 << r->bin_org_bits) / (float)(1 << src->bin_org_bits);   // (this renderer's own bin settings)
+		r->staged_sv.bin_org_bits = r->bin_org_bits; r->staged_sv.bin_dir_bits = r->bin_dir_bits;
 		for (int k = 0; k < 3; ++k) { r->world_min[k] = src->world_min[k]; r->world_max[k] = src->world_max[k]; }
 		r->scene_stats = src->scene_stats;
 	}
@@ -243,6 +255,8 @@ static int ensure_wave(rtb_renderer* r, size_t paths, uint32_t depth) {
 	size_t o_t0 = take(P * 16), o_t1 = take(P * 16), o_hit = take(P * 8), o_con = take(P * 16);
 	size_t o_live = take((depth + 2) * 4), o_work = take(2 * (depth + 2) * 4), o_batch = take(256), o_tot = take(256);
 	size_t o_tex = take(P * 32), o_ntex = take((depth + 2) * 4);
+	const size_t nbins = (size_t)1 << (3 * r->bin_org_bits + 2 * r->bin_dir_bits);
+	size_t o_bcnt = take(nbins * 4), o_bcur = take(nbins * 4);
 	CUDA_TRY(cudaMalloc(&r->d_wave, off));
 	CUDA_TRY(cudaMemset(r->d_wave, 0, off));
 	uint8_t* b = static_cast<uint8_t*>(r->d_wave);
@@ -252,6 +266,8 @@ static int ensure_wave(rtb_renderer* r, size_t paths, uint32_t depth) {
 	r->wv.hit = (int2*)(b + o_hit); r->wv.contrib = (float4*)(b + o_con);
 	r->wv.n_live = (uint32_t*)(b + o_live); r->wv.work = (uint32_t*)(b + o_work);
 	r->wv.tex_work = (float4*)(b + o_tex); r->wv.n_tex = (uint32_t*)(b + o_ntex);
+	r->wv.bin_count = (uint32_t*)(b + o_bcnt); r->wv.bin_cursor = (uint32_t*)(b + o_bcur);
+	r->wv.capacity = (uint32_t)P; r->wv.n_bins = (uint32_t)nbins;
 	r->wv.batch_index = (uint32_t*)(b + o_batch); r->wv.tail_from = r->wv.batch_index + 1; r->wv.totals = (unsigned long long*)(b + o_tot);
 	r->wave_paths = P; r->wave_depth = depth;
 	return RTB_OK;
@@ -267,18 +283,30 @@ static bool tail_checkpoint(uint32_t b) {
 }
 static uint32_t count_tail_checkpoints(uint32_t depth) { uint32_t c = 0; for (uint32_t b = 0; b < depth; ++b) c += tail_checkpoint(b) ? 1 : 0; return c; }
 
+// Which bounces' queues are binned before they are traversed (bit b of the mask), and how finely: RTB_BIN_MASK (hex),
+// RTB_BIN_BITS=<origin bits per axis>,<direction bits per axis> (0,0 = off).
+static bool binned_bounce(const rtb_renderer* r, uint32_t b) {
+	if (r->sv.bin_org_bits + r->sv.bin_dir_bits == 0 || b == 0) return false;
+	return b < 64 ? ((r->bin_mask >> b) & 1ull) != 0 : false;
+}
+static uint32_t count_binned_bounces(const rtb_renderer* r, uint32_t depth) { uint32_t c = 0; for (uint32_t b = 1; b < depth; ++b) c += binned_bounce(r, b) ? 1 : 0; return c; }
+
 static void enqueue_batch(rtb_renderer* r, const BatchParams& bp, cudaStream_t st) {
 	prof_begin(r, 0, st); launch_generate(bp, r->cam, r->wv, r->lc, st); prof_end(r, st);
-	// EXPERIMENT (profiling renders only, rtb_sort.cu): RTB_SORT_EXPERIMENT=<mode>[,<first bounce>,<last bounce>]
-	int sort_mode = 0; unsigned long long sort_mask = 0x1FEull;   // which bounces' queues are sorted before they are traversed (bit b)
+	// EXPERIMENT (profiling renders only, rtb_sort.cu): RTB_SORT_EXPERIMENT=<mode>,<hex mask of bounces>
+	int sort_mode = 0; unsigned long long sort_mask = 0x1FEull;
 	if (r->profiling) if (const char* e = getenv("RTB_SORT_EXPERIMENT")) { unsigned m = 0; unsigned long long k2 = 0; int k = sscanf(e, "%u,%llx", &m, &k2); if (k >= 1) sort_mode = (int)m; if (k >= 2) sort_mask = k2; }
+	int q = 0;   // the queue that holds the rays of bounce b
 	for (uint32_t b = 0; b < bp.max_depth; ++b) {
-		if (sort_mode && b < 64 && ((sort_mask >> b) & 1ull)) experimental_sort_queue(r, b, sort_mode, r->world_min, r->world_max);
-		if (r->tail_threshold && tail_checkpoint(b)) { prof_begin(r, 4, st); launch_tail(r->sv, bp, r->wv, b, r->tail_threshold, r->lc, st); prof_end(r, st); }
-		prof_begin(r, 1, st); launch_traverse(r->sv, bp, r->wv, b, r->lc, st); prof_end(r, st);
-		prof_begin(r, 2, st); launch_shade(r->sv, bp, r->wv, b, r->lc, st);
-		if (r->sv.has_deferred_tex && b + 1 < bp.max_depth) launch_texture(r->sv, r->wv, b, r->lc, st);
+		if (sort_mode && b < 64 && ((sort_mask >> b) & 1ull)) experimental_sort_queue(r, b, q, sort_mode, r->world_min, r->world_max);
+		if (r->tail_threshold && tail_checkpoint(b)) { prof_begin(r, 4, st); launch_tail(r->sv, bp, r->wv, b, q, r->tail_threshold, r->lc, st); prof_end(r, st); }
+		prof_begin(r, 1, st); launch_traverse(r->sv, bp, r->wv, b, q, r->lc, st); prof_end(r, st);
+		const bool bin_next = b + 1 < bp.max_depth && binned_bounce(r, b + 1);
+		prof_begin(r, 2, st); launch_shade(r->sv, bp, r->wv, b, q, bin_next ? 1 : 0, r->lc, st);
+		if (r->sv.has_deferred_tex && b + 1 < bp.max_depth) launch_texture(r->sv, r->wv, b, q ^ 1, r->lc, st);
 		prof_end(r, st);
+		if (bin_next) { prof_begin(r, 5, st); launch_bin_rays(r->sv, r->wv, b + 1, q ^ 1, r->lc, st); prof_end(r, st); }   // ... and back into queue q
+		else q ^= 1;
 	}
 	prof_begin(r, 3, st); launch_accumulate(bp, r->wv, r->d_accum, r->d_accum2, r->lc, st); prof_end(r, st);
 }
@@ -339,7 +367,7 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 
 	const uint32_t n_batches = spp ? (uint32_t)((spp + S - 1) / S) : 0;
 	const uint64_t launches_per_batch = 3 + 2ull * bp.max_depth + (r->tail_threshold ? count_tail_checkpoints(bp.max_depth) : 0) +
-	                                    (r->sv.has_deferred_tex ? bp.max_depth - 1 : 0);
+	                                    (r->sv.has_deferred_tex ? bp.max_depth - 1 : 0) + 2ull * count_binned_bounces(r, bp.max_depth);
 	const bool use_graph = getenv("RTB_NO_GRAPH") == nullptr && n_batches > 0 && !r->profiling;
 	if (use_graph) {
 		bool reuse = r->graph_valid && memcmp(&r->graph_bp, &bp, sizeof bp) == 0 && memcmp(&r->graph_cam, &r->cam, sizeof r->cam) == 0 &&
@@ -521,7 +549,7 @@ int rtb_get_profile(rtb_renderer* r, rtb_profile* out) {
 	memset(out, 0, sizeof *out);
 	CUDA_TRY(cudaSetDevice(r->device));
 	CUDA_TRY(cudaStreamSynchronize(r->stream));
-	double ms[5] = {0, 0, 0, 0, 0}; uint64_t cnt[5] = {0, 0, 0, 0, 0};
+	double ms[6] = {0, 0, 0, 0, 0, 0}; uint64_t cnt[6] = {0, 0, 0, 0, 0, 0};
 	for (size_t i = 0; i < r->prof_used; ++i) {
 		float t = 0.0f;
 		CUDA_TRY(cudaEventElapsedTime(&t, r->prof_events[2 * i], r->prof_events[2 * i + 1]));
@@ -529,6 +557,7 @@ int rtb_get_profile(rtb_renderer* r, rtb_profile* out) {
 	}
 	out->generate_ms = ms[0]; out->traverse_ms = ms[1]; out->shade_ms = ms[2]; out->accumulate_ms = ms[3];
 	out->tail_ms = ms[4]; out->tail_launches = cnt[4];
+	out->bin_ms = ms[5]; out->bin_launches = 2 * cnt[5];
 	out->generate_launches = cnt[0]; out->traverse_launches = cnt[1]; out->shade_launches = cnt[2]; out->accumulate_launches = 2 * cnt[3];
 	r->prof_used = 0;
 	return RTB_OK;
@@ -563,6 +592,19 @@ int rtb_reset_counters(rtb_renderer* r) {
 	if (r->d_wave) CUDA_TRY(cudaMemset(r->wv.totals, 0, 2 * sizeof(unsigned long long)));
 	r->launches = 0; r->batches = 0;
 	return RTB_OK;
+}
+
+int rtb_debug_bounds_report(rtb_renderer* r, uint64_t* violations_out, int cap, uint64_t* checks_out) {
+	if (!r || !violations_out || cap < 0) return fail(RTB_ERR_INVALID, "rtb_debug_bounds_report: bad argument");
+	CUDA_TRY(cudaSetDevice(r->device));
+	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	unsigned long long v[RTB_BOUNDS_CLASSES] = {0}, checks = 0;
+	const int rc = debug_bounds_report(v, &checks);
+	if (rc == 0) return fail(RTB_ERR_UNSUPPORTED, "rtb_debug_bounds_report: this library was not built with -DRTB_DEBUG_BOUNDS=1 (use librtb200_debug.so)");
+	if (rc < 0) return fail(RTB_ERR_CUDA, "rtb_debug_bounds_report: cannot read the counters");
+	for (int i = 0; i < cap; ++i) violations_out[i] = i < RTB_BOUNDS_CLASSES ? v[i] : 0;
+	if (checks_out) *checks_out = checks;
+	return RTB_BOUNDS_CLASSES;
 }
 
 int rtb_trace_rays(rtb_renderer* r, const rtb_ray* rays, size_t n, rtb_hit* hits_out) {

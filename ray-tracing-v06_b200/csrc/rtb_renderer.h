@@ -58,6 +58,8 @@ struct rtb_renderer {
 	float4 *graph_accum = nullptr;
 
 	uint64_t launches = 0, batches = 0;
+	int bin_org_bits = 4, bin_dir_bits = 3;                  // ray binning: 2^(3 * 4 + 2 * 3) = 262,144 bins
+	unsigned long long bin_mask = 0x0000111111111FFEull;      // bounces whose queue is binned before it is traversed
 	uint32_t tail_threshold = 0;   // live-queue length below which the fused tail kernel takes a batch over
 
 	// optional per-launch event timing (rtb_renderer_set_profiling)
@@ -71,7 +73,7 @@ struct rtb_renderer {
 // Resolve (mean -> clamp -> sqrt) of an arbitrary accumulator on this renderer's device and stream (rtb_multi.cu resolves
 // the cross-device total with it).
 int rtb_resolve_from(rtb_renderer* r, const float4* accum, void* d_out, void* user_stream);
-namespace rtb { int experimental_sort_queue(rtb_renderer* r, uint32_t bounce, int mode, const float* world_min, const float* world_max); }   // rtb_sort.cu
+namespace rtb { int experimental_sort_queue(rtb_renderer* r, uint32_t bounce, int q, int mode, const float* world_min, const float* world_max); }   // rtb_sort.cu
 int rtb_quantize_from(rtb_renderer* r, const float4* accum, uint8_t* host_rgb, int flip_rows);
 
 #endif

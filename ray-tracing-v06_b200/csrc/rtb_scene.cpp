@@ -1016,6 +1016,19 @@ int flatten(rtb_scene& s, FlatScene& out, const GpuBuildContext* gpu) {
 		out.root_ref = 0;
 	}
 	for (int k = 0; k < 3; ++k) { out.world_min[k] = nodes[root_idx].bmin[k]; out.world_max[k] = nodes[root_idx].bmax[k]; }
+	// The ray-binning grid spans the centres of the primitives' boxes, not their extents: one huge primitive (a
+	// 1000-unit ground sphere under a scene a few units wide) must not decide the cell size.
+	for (int k = 0; k < 3; ++k) { out.bin_min[k] = INFINITY; out.bin_max[k] = -INFINITY; }
+	for (const Box3& b : fl.prim_boxes)
+		for (int k = 0; k < 3; ++k) { const float c = 0.5f * (b.mn[k] + b.mx[k]); out.bin_min[k] = std::min(out.bin_min[k], c); out.bin_max[k] = std::max(out.bin_max[k], c); }
+	for (int k = 0; k < 3; ++k) {   // a margin of 5 %, and never thinner than a thousandth of the largest side
+		const float ext = out.bin_max[k] - out.bin_min[k];
+		out.bin_min[k] -= 0.05f * ext; out.bin_max[k] += 0.05f * ext;
+	}
+	{
+		const float widest = std::max(std::max(out.bin_max[0] - out.bin_min[0], out.bin_max[1] - out.bin_min[1]), out.bin_max[2] - out.bin_min[2]);
+		for (int k = 0; k < 3; ++k) if (out.bin_max[k] - out.bin_min[k] < 1e-3f * widest || !(out.bin_max[k] > out.bin_min[k])) { out.bin_min[k] -= 0.5e-3f * widest + 1e-6f; out.bin_max[k] += 0.5e-3f * widest + 1e-6f; }
+	}
 	s.world_nodes = std::move(nodes); s.world_root = root_idx;
 
 	}

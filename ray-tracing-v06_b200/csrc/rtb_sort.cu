@@ -56,7 +56,7 @@ struct SortScratch { uint32_t *keys = nullptr, *keys2 = nullptr, *idx = nullptr,
 static SortScratch g_scratch;
 
 // Reorders queue `q` (0/1) of bounce `bounce`: synchronises, so only for profiling renders.
-int experimental_sort_queue(rtb_renderer* r, uint32_t bounce, int mode, const float* world_min, const float* world_max) {
+int experimental_sort_queue(rtb_renderer* r, uint32_t bounce, int q, int mode, const float* world_min, const float* world_max) {
 	cudaStream_t st = r->stream;
 	uint32_t n = 0;
 	CUDA_TRY(cudaMemcpyAsync(&n, r->wv.n_live + bounce, 4, cudaMemcpyDeviceToHost, st));
@@ -76,7 +76,6 @@ int experimental_sort_queue(rtb_renderer* r, uint32_t bounce, int mode, const fl
 	const int dir_bits = mode & 15, org_bits = (mode >> 4) & 15, dir_major = (mode >> 8) & 1;
 	SortBounds sb;
 	for (int k = 0; k < 3; ++k) { sb.mn[k] = world_min[k]; const float e = world_max[k] - world_min[k]; sb.inv[k] = e > 0.0f ? 1.0f / e : 0.0f; }
-	const int q = bounce & 1;
 	sort_keys_kernel<<<148 * 8, 256, 0, st>>>(r->wv.ray_o[q], r->wv.ray_d[q], r->wv.n_live + bounce, s.keys, s.idx, dir_bits, org_bits, dir_major, sb);
 	const int bits = 2 * dir_bits + 3 * org_bits;
 	size_t tb = s.temp_bytes;

@@ -80,6 +80,7 @@ struct FlatScene {
 	int32_t builder = 0;                 // rtb_world_bvh_mode that produced the tree (3 = median fallback)
 	int32_t n_items = 0;                 // BVH leaves
 	float world_min[3] = {0, 0, 0}, world_max[3] = {0, 0, 0};   // bounds of the world BVH
+	float bin_min[3] = {0, 0, 0}, bin_max[3] = {0, 0, 0};       // bounds of the primitives' box centres: the ray-binning grid
 	float flatten_ms = 0.0f, bvh_build_ms = 0.0f;
 };
 

@@ -266,3 +266,38 @@ def test_oracle_has_not_drifted(rtb, orc):
         acc, _, rays = orc.OracleScene(s.serialize()).render(s.info.camera, 32, 18, 0, 2, 8, seed=1984)
         assert rays == int(gold[name + "__rays"][0]), name
         np.testing.assert_allclose(acc, gold[name], rtol=1e-6, atol=1e-6, err_msg=name)
+
+
+# ---------------------------------------------------------------- analytic pins for features the reference does not contain
+
+def _oracle_trace(rtb, orc):
+    return lambda scene, rays: orc.OracleScene(scene.serialize()).trace_rays(rays, rtb.HIT_DTYPE)
+
+
+def _oracle_render(orc):
+    return lambda scene, cam, w, h, spp, depth: orc.OracleScene(scene.serialize()).render(cam, w, h, 0, spp, depth, seed=5)[0]
+
+
+def test_analytic_quad_alpha_beta(rtb, orc):
+    import analytic
+    analytic.check_quad_alpha_beta(rtb, _oracle_trace(rtb, orc))
+
+
+def test_analytic_rotate_y_quarter_turn(rtb, orc):
+    import analytic
+    analytic.check_rotate_y_quarter_turn(rtb, _oracle_trace(rtb, orc))
+
+
+def test_analytic_sphere_uv(rtb, orc):
+    import analytic
+    analytic.check_sphere_uv(rtb, _oracle_trace(rtb, orc))
+
+
+def test_analytic_checker_truncation(rtb, orc):
+    import analytic
+    analytic.check_checker_at_negative_coordinates(rtb, _oracle_trace(rtb, orc), _oracle_render(orc))
+
+
+def test_analytic_image_texture(rtb, orc):
+    import analytic
+    analytic.check_image_texture_lookup(rtb, _oracle_render(orc))

@@ -106,3 +106,117 @@ def test_multi_renderer_two_devices(rtb, mode):
     m.render(W, H, 0, 7, D, seed=3); m.synchronize()
     r.render(W, H, 0, 7, D, seed=3)
     np.testing.assert_allclose(m.download_accum(), r.download_accum(), rtol=1e-5, atol=1e-5)
+
+
+def _read_png(path):
+    """Minimal PNG reader (8-bit RGB, filter 0 rows): signature, IHDR, IDAT through zlib, CRCs checked."""
+    import struct
+    import zlib
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, w, h = 8, b"", 0, 0
+    while pos < len(raw):
+        n, typ = struct.unpack(">I4s", raw[pos:pos + 8]); data = raw[pos + 8:pos + 8 + n]
+        crc, = struct.unpack(">I", raw[pos + 8 + n:pos + 12 + n])
+        assert crc == (zlib.crc32(typ + data) & 0xFFFFFFFF), typ
+        if typ == b"IHDR":
+            w, h, depth, colour, comp, filt, inter = struct.unpack(">IIBBBBB", data); assert (depth, colour, comp, filt, inter) == (8, 2, 0, 0, 0)
+        elif typ == b"IDAT":
+            idat += data
+        pos += 12 + n
+    rows = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + 3 * w)
+    assert (rows[:, 0] == 0).all()
+    return rows[:, 1:].reshape(h, w, 3)
+
+
+def _app(*args):
+    import subprocess
+    from conftest import ROOT
+    return subprocess.run([str(ROOT / "ray-tracing-v06_b200" / "rtb_app"), *[str(a) for a in args]], check=True, capture_output=True, text=True).stdout
+
+
+def test_cli_png_seed_and_checkpoint(rtb, tmp_path):
+    """rtb_app: the PNG carries exactly the device-quantised picture (uint8(x * 255.999), rows flipped, FirstApp.cpp:108-122);
+    --seed changes the image and is reproducible; --checkpoint / --resume continue a render bit for bit."""
+    W, H, D = 96, 64, 16
+    scene = rtb.Scene.named("book2_cornell"); r = rtb.Renderer(0); r.set_scene(scene); r.set_camera(scene.info.camera)
+    png = tmp_path / "a.png"
+    _app("book2_cornell", "--width", W, "--height", H, "--spp", 8, "--depth", D, "--seed", 77, "--out", png)
+    img = _read_png(png)
+    r.render(W, H, 0, 8, D, seed=77)
+    assert np.array_equal(img, r.download_rgb8())
+    _app("book2_cornell", "--width", W, "--height", H, "--spp", 8, "--depth", D, "--seed", 78, "--out", tmp_path / "b.png")
+    assert not np.array_equal(_read_png(tmp_path / "b.png"), img)
+    # 3 samples + checkpoint, then 5 more from the checkpoint == the library doing the same two renders
+    ck = tmp_path / "c.rtba"
+    _app("book2_cornell", "--width", W, "--height", H, "--spp", 3, "--depth", D, "--seed", 77, "--checkpoint", ck, "--out", tmp_path / "c3.png")
+    log = _app("book2_cornell", "--width", W, "--height", H, "--spp", 5, "--depth", D, "--seed", 77, "--resume", ck, "--out", tmp_path / "c8.png")
+    assert "Resuming at sample 3" in log
+    r.render(W, H, 0, 3, D, seed=77); r.render(W, H, 3, 8, D, seed=77, clear=False)
+    assert np.array_equal(_read_png(tmp_path / "c8.png"), r.download_rgb8())
+    # ppm and pfm still work
+    _app("book2_cornell", "--width", W, "--height", H, "--spp", 2, "--depth", D, "--out", tmp_path / "d.pfm")
+    assert (tmp_path / "d.pfm").read_bytes().startswith(f"PF\n{W} {H}\n-1.0\n".encode())
+
+
+def test_cli_two_gpus(rtb, tmp_path):
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    W, H, D = 96, 96, 16
+    log = _app("book2_final", "--width", W, "--height", H, "--spp", 16, "--depth", D, "--gpus", 2, "--out", tmp_path / "m.png")
+    assert "on 2 GPUs" in log
+    one = _app("book2_final", "--width", W, "--height", H, "--spp", 16, "--depth", D, "--out", tmp_path / "s.png")
+    a, b = _read_png(tmp_path / "m.png").astype(np.int32), _read_png(tmp_path / "s.png").astype(np.int32)
+    assert np.abs(a - b).max() <= 1          # same samples, sums associated differently: at most one 8-bit step
+    # the Renderer mirror picks the GPUs up from RTB_GPUS (book2_bouncing goes through Renderer::MakeRenderer)
+    import os
+    import subprocess
+    from conftest import ROOT
+    env = dict(os.environ, RTB_GPUS="2")
+    out = subprocess.run([str(ROOT / "ray-tracing-v06_b200" / "rtb_app"), "book2_bouncing", "--width", "128", "--height", "72", "--spp", "8", "--depth", "12",
+                          "--out", str(tmp_path / "mm.png")], check=True, capture_output=True, text=True, env=env).stdout
+    assert "2 GPUs" in out
+    _app("book2_bouncing", "--width", 128, "--height", 72, "--spp", 8, "--depth", 12, "--out", tmp_path / "ss.png")
+    assert np.abs(_read_png(tmp_path / "mm.png").astype(np.int32) - _read_png(tmp_path / "ss.png").astype(np.int32)).max() <= 1
+
+
+def test_debug_bounds_build_sees_no_violation(rtb):
+    """compute-sanitizer is not available on this pool, so memory safety of the kernels is checked by the kernels
+    themselves: librtb200_debug.so (-DRTB_DEBUG_BOUNDS=1) tests every index it forms - traversal stack slot, node,
+    primitive record, material, texture / texel, queue slot, path id, ray bin - against the size of what it indexes.  Every
+    registered scene is rendered (small image, several batches, deep paths, binning on) and traced through that build in a
+    separate process; no class may count a single violation."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    if not rtb.DEBUG_LIB_PATH.exists():
+        pytest.skip("librtb200_debug.so not built")
+    code = r'''
+import importlib, json, sys
+import numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+rtb = importlib.import_module("ray-tracing-v06_b200")
+from helpers import camera_rays, random_rays
+r = rtb.Renderer(0); total = None
+for name in rtb.scene_names():
+    s = rtb.Scene.named(name); r.set_scene(s); r.set_camera(s.info.camera)
+    r.render(72, 56, 0, 6, 60, seed=9, samples_per_batch=4, variance=True)
+    r.render(40, 40, 6, 9, 8, seed=9)
+    r.trace_rays(np.concatenate([camera_rays(rtb, s.info.camera, 64, 64, "renderer"), random_rays(rtb, 20000, -50, 300, seed=1)]))
+    if name == "book2_final":
+        s.set_world_bvh(rtb.WORLD_BVH_GPU_LBVH); r.set_scene(s); r.render(64, 64, 0, 4, 40, seed=2)
+    r.synchronize()
+print("REPORT " + json.dumps(r.debug_bounds_report()))
+''' % (str(ROOT), str(ROOT / "tests"))
+    env = dict(os.environ, RTB_LIB=str(rtb.DEBUG_LIB_PATH))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rep = json.loads([l for l in out.stdout.splitlines() if l.startswith("REPORT ")][-1][7:])
+    print("bounds report:", rep)
+    assert rep.pop("rays_checked") > 100_000
+    assert all(v == 0 for v in rep.values()), rep
+    r0 = rtb.Renderer(0)
+    with pytest.raises(rtb.RtbError, match="RTB_DEBUG_BOUNDS"):
+        r0.debug_bounds_report()                     # the release library says so instead of reporting zeros

@@ -618,3 +618,32 @@ def test_thin_far_geometry_is_never_culled(rtb, orc, renderer):
     lost = (o_hits["object"] >= 0) & (g["object"] < 0)
     assert not lost.any(), f"{lost.sum()} hits of the oracle were culled by the slab test"
     assert _compare_hits(rtb, g, o_hits, exact=True, max_tie_frac=0.02) > 20_000
+
+
+# ---------------------------------------------------------------- analytic pins (tests/analytic.py) through the CUDA path
+
+def _gpu_trace(renderer):
+    def trace(scene, rays):
+        renderer.set_scene(scene)
+        return renderer.trace_rays(rays)
+    return trace
+
+
+def _gpu_render(renderer):
+    def render(scene, cam, w, h, spp, depth):
+        renderer.set_scene(scene); renderer.set_camera(cam)
+        renderer.render(w, h, 0, spp, depth, seed=5)
+        return renderer.download_accum()
+    return render
+
+
+def test_analytic_pins_gpu(rtb, renderer):
+    """The hand-derived known answers for the features the reference lacks (quad alpha/beta and (u,v), rotate_y at 90
+    degrees, sphere (u,v) at the poles and the seam, the reference's truncating checker at negative coordinates, image
+    texel lookup), through rtb_trace_rays / rtb_render."""
+    import analytic
+    analytic.check_quad_alpha_beta(rtb, _gpu_trace(renderer))
+    analytic.check_rotate_y_quarter_turn(rtb, _gpu_trace(renderer))
+    analytic.check_sphere_uv(rtb, _gpu_trace(renderer))
+    analytic.check_checker_at_negative_coordinates(rtb, _gpu_trace(renderer), _gpu_render(renderer))
+    analytic.check_image_texture_lookup(rtb, _gpu_render(renderer))

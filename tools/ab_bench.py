@@ -25,7 +25,7 @@ def run(name, steps=6, warmup=3, extra_env=None):
     j = json.loads(out.stdout.strip().splitlines()[-1])
     ks = j.get("kernel_split") or {}
     return {"name": name, "mrays_per_s": j["value"], "ms_per_step": j["ms_per_step"], "e2e": j["e2e"]["value"], "traverse_ms": ks.get("traverse_ms"),
-            "shade_ms": ks.get("shade_ms"), "generate_ms": ks.get("generate_ms"), "accumulate_ms": ks.get("accumulate_ms"), "tail_ms": ks.get("tail_ms"),
+            "shade_ms": ks.get("shade_ms"), "generate_ms": ks.get("generate_ms"), "accumulate_ms": ks.get("accumulate_ms"), "tail_ms": ks.get("tail_ms"), "bin_ms": ks.get("bin_ms"),
             "sm_mhz": (j.get("clocks") or {}).get("sm_mhz"), "reasons": (j.get("clocks") or {}).get("reasons")}
 
 

@@ -29,12 +29,19 @@ if __name__ == "__main__":
     ms, cls = r.profile_launches(); prof = r.profile(); r.set_profiling(False)
     q = r.queue_lengths()
     trav = ms[cls == 1]; shade = ms[cls == 2]
+    bins = {}                                   # a binning launch sits between shade(b - 1) and traverse(b): it belongs to bounce b
+    nb = 0
+    for t, c in zip(ms, cls):
+        if c == 1:
+            nb += 1
+        elif c == 5:
+            bins[nb] = float(t)
     rows = []
     for b in range(min(len(trav), len(q))):
         n = int(q[b])
-        rows.append({"bounce": b, "rays": n, "traverse_us": round(float(trav[b]) * 1e3, 1), "shade_us": round(float(shade[b]) * 1e3, 1),
+        rows.append({"bounce": b, "rays": n, "traverse_us": round(float(trav[b]) * 1e3, 1), "shade_us": round(float(shade[b]) * 1e3, 1), "bin_us": round(bins.get(b, 0.0) * 1e3, 1),
                      "traverse_grays_s": round(n / (float(trav[b]) * 1e-3) / 1e9, 2) if trav[b] > 0 else None,
                      "shade_grays_s": round(n / (float(shade[b]) * 1e-3) / 1e9, 2) if shade[b] > 0 else None})
     out = {"scene": args.scene, "width": W, "height": H, "spp": args.spp, "depth": D, "traverse_ms": prof.traverse_ms, "shade_ms": prof.shade_ms,
-           "generate_ms": prof.generate_ms, "accumulate_ms": prof.accumulate_ms, "tail_ms": prof.tail_ms, "rays": int(sum(int(x) for x in q)), "bounces": rows}
+           "generate_ms": prof.generate_ms, "accumulate_ms": prof.accumulate_ms, "tail_ms": prof.tail_ms, "bin_ms": prof.bin_ms, "rays": int(sum(int(x) for x in q)), "bounces": rows}
     print(json.dumps(out, indent=1))
