@@ -48,6 +48,32 @@ def lib():
     return _lib
 
 
+class Camera(C.Structure):
+    """rtb_camera (include/rtb.h), declared here too so that the reference arm of bench.py needs nothing from the product."""
+    _fields_ = [("kind", C.c_int32), ("o", C.c_float * 3), ("u", C.c_float * 3), ("v", C.c_float * 3), ("w", C.c_float * 3),
+                ("viewport_width", C.c_float), ("viewport_height", C.c_float), ("lens_radius", C.c_float), ("focus_dist", C.c_float),
+                ("t0", C.c_float), ("t1", C.c_float)]
+
+
+def camera_to_dict(cam) -> dict:
+    """Bit-exact (hex floats) description of an rtb_camera, for the committed scene fixtures."""
+    d = {"kind": int(cam.kind)}
+    for k in ("o", "u", "v", "w"):
+        d[k] = [float(x).hex() for x in getattr(cam, k)]
+    for k in ("viewport_width", "viewport_height", "lens_radius", "focus_dist", "t0", "t1"):
+        d[k] = float(getattr(cam, k)).hex()
+    return d
+
+
+def camera_from_dict(d: dict) -> Camera:
+    cam = Camera(); cam.kind = d["kind"]
+    for k in ("o", "u", "v", "w"):
+        setattr(cam, k, (C.c_float * 3)(*[float.fromhex(x) for x in d[k]]))
+    for k in ("viewport_width", "viewport_height", "lens_radius", "focus_dist", "t0", "t1"):
+        setattr(cam, k, float.fromhex(d[k]))
+    return cam
+
+
 class OracleScene:
     def __init__(self, blob: bytes):
         self._blob = blob

@@ -868,20 +868,8 @@ __device__ __forceinline__ uint32_t ray_bin(const SceneView& sv, const float4& o
 	}
 	return key;
 }
-// One atomic per distinct bin among the active lanes of a warp; returns this lane's slot (base of its bin's run + rank).
-__device__ __forceinline__ uint32_t warp_bin_add(uint32_t* counters, uint32_t counters_size, uint32_t bin) {
-	RTB_CHECK(bin < counters_size, RTB_BOUNDS_BIN);
-	const uint32_t act = __activemask();
-	const uint32_t peers = __match_any_sync(act, bin);
-	const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
-	uint32_t base = 0;
-	if (lane == leader) base = atomicAdd(counters + bin, (uint32_t)__popc(peers));
-	base = __shfl_sync(peers, base, leader);
-	return base + __popc(peers & ((1u << lane) - 1u));
-}
-
 __global__ void __launch_bounds__(SHADE_THREADS)
-shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce, int q, int count_bins) {
+shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce, int q) {
 	__shared__ uint32_t s_chunk, s_base;
 	__shared__ uint32_t s_warp[SHADE_THREADS / 32];
 	if (bounce >= *wv.tail_from) return;
@@ -927,7 +915,6 @@ shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce, int q, 
 			const uint32_t pos = s_base + s_warp[warp] + __popc(mask & ((1u << lane) - 1u));
 			RTB_CHECK(pos < wv.capacity && pos < n, RTB_BOUNDS_QUEUE);
 			stq(wo + pos, no); stq(wd + pos, nd); stq(wt + pos, make_float4(nthr.x, nthr.y, nthr.z, 0.0f));
-			if (count_bins) warp_bin_add(wv.bin_count, wv.n_bins, ray_bin(sv, no, nd));
 			// texture work list: (p, queue slot), (u, v, -, texture id)
 			const bool defer = dt.tex >= 0;
 			const uint32_t act = __activemask();
@@ -972,48 +959,148 @@ texture_kernel(SceneView sv, WaveView wv, uint32_t bounce, int q_out) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// binning: shade counted the rays of the next bounce per bin; bin_scan turns the counts into the first slot of every bin
-// (and leaves the counters zero for their next use), bin_permute moves every ray to the next free slot of its bin in the
-// other queue.  Where a ray sits in a queue changes nothing about the image - contributions are stored by path id and
-// summed per pixel in sample order - only which rays share a warp.
+// binning: a counting sort of the live queue by ray_bin between shade(b - 1) and traverse(b), in three launches.
+//   bin_count    rays per bin
+//   bin_scan     exclusive prefix sums of the counts = the first slot of every bin
+//   bin_permute  every ray moves to the next free slot of its bin in the other queue
+// Rays pile up in few bins (a third of the late-bounce rays of the Book 2 final scene scatter inside one sphere of
+// smoke), so neither kernel sends one global atomic per ray: each block aggregates the keys of its rays in a small
+// shared-memory hash table first - same-address atomics are cheap there - and touches a global counter once per distinct
+// key.  Where a ray sits in a queue changes nothing about the image - contributions are stored by path id and summed per
+// pixel in sample order - only which rays share a warp.
 
+#define BIN_THREADS 256
+#define BIN_ITEMS 4                                  // rays per thread per tile
+#define BIN_TILE (BIN_THREADS * BIN_ITEMS)
+#define BIN_SLOTS 2048                               // hash slots per block: at most half full with one tile's keys
+#define BIN_EMPTY 0xFFFFFFFFu
+
+// Finds or claims the slot of `key` and counts one ray in it (linear probing; the table never fills: <= BIN_TILE keys).
+__device__ __forceinline__ uint32_t bin_table_add(uint32_t* s_key, uint32_t* s_cnt, uint32_t key) {
+	uint32_t h = (key * 2654435761u) >> (32 - 11);  // Fibonacci hash to log2(BIN_SLOTS) = 11 bits
+	for (;;) {
+		const uint32_t prev = atomicCAS(s_key + h, BIN_EMPTY, key);
+		if (prev == BIN_EMPTY || prev == key) { atomicAdd(s_cnt + h, 1u); return h; }
+		h = (h + 1u) & (BIN_SLOTS - 1u);
+	}
+}
+
+__global__ void __launch_bounds__(BIN_THREADS)
+bin_count_kernel(SceneView sv, WaveView wv, uint32_t bounce, int q) {
+	__shared__ uint32_t s_key[BIN_SLOTS], s_cnt[BIN_SLOTS];
+	if (bounce >= *wv.tail_from) return;
+	const uint32_t n = wv.n_live[bounce];
+	if (n == 0) return;
+	const float4* __restrict__ ro = q ? wv.ray_o[1] : wv.ray_o[0];
+	const float4* __restrict__ rd = q ? wv.ray_d[1] : wv.ray_d[0];
+	for (uint32_t s = threadIdx.x; s < BIN_SLOTS; s += BIN_THREADS) { s_key[s] = BIN_EMPTY; s_cnt[s] = 0u; }
+	__syncthreads();
+	for (uint32_t base = blockIdx.x * BIN_TILE; base < n; base += gridDim.x * BIN_TILE) {
+#pragma unroll
+		for (int k = 0; k < BIN_ITEMS; ++k) {
+			const uint32_t i = base + k * BIN_THREADS + threadIdx.x;
+			if (i < n) bin_table_add(s_key, s_cnt, ray_bin(sv, ldq(ro + i), ldq(rd + i)));
+		}
+		__syncthreads();
+		// one global atomic per distinct key of the tile, then the table is empty again
+		for (uint32_t s = threadIdx.x; s < BIN_SLOTS; s += BIN_THREADS) {
+			const uint32_t key = s_key[s];
+			if (key != BIN_EMPTY) { RTB_CHECK(key < wv.n_bins, RTB_BOUNDS_BIN); atomicAdd(wv.bin_count + key, s_cnt[s]); s_key[s] = BIN_EMPTY; s_cnt[s] = 0u; }
+		}
+		__syncthreads();
+	}
+}
+
+// Block b owns bins [b * 4096, (b + 1) * 4096): it adds up everything before them (the counts are re-read from L2 - at
+// most 1 MB - instead of passing block totals around), then scans its own.  The counters are zeroed by bin_permute.
 #define BIN_SCAN_THREADS 1024
+#define BIN_SCAN_PER_BLOCK 4096
 __global__ void __launch_bounds__(BIN_SCAN_THREADS)
-bin_scan_kernel(WaveView wv, uint32_t bounce, uint32_t nbins) {
+bin_scan_kernel(WaveView wv, uint32_t bounce) {
 	__shared__ uint32_t s_part[BIN_SCAN_THREADS];
-	if (bounce >= *wv.tail_from || wv.n_live[bounce] == 0) return;   // (shade did not count either)
-	const uint32_t per = (nbins + BIN_SCAN_THREADS - 1) / BIN_SCAN_THREADS;
-	const uint32_t b0 = min(threadIdx.x * per, nbins), b1 = min(b0 + per, nbins);
+	__shared__ uint32_t s_before;
+	if (bounce >= *wv.tail_from || wv.n_live[bounce] == 0) return;
+	const uint32_t first = blockIdx.x * BIN_SCAN_PER_BLOCK;
 	uint32_t sum = 0;
-	for (uint32_t b = b0; b < b1; ++b) sum += wv.bin_count[b];
+	for (uint32_t b = threadIdx.x; b < first; b += BIN_SCAN_THREADS) sum += wv.bin_count[b];
 	s_part[threadIdx.x] = sum;
 	__syncthreads();
-	for (uint32_t off = 1; off < BIN_SCAN_THREADS; off <<= 1) {        // inclusive scan of the per-thread sums
+	for (uint32_t off = BIN_SCAN_THREADS / 2; off > 0; off >>= 1) {
+		if (threadIdx.x < off) s_part[threadIdx.x] += s_part[threadIdx.x + off];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) s_before = s_part[0];
+	__syncthreads();
+	// own bins: 4 consecutive bins per thread (one 16-byte load), block-wide inclusive scan of the per-thread sums
+	const uint32_t b0 = first + 4u * threadIdx.x;
+	uint4 c = make_uint4(0, 0, 0, 0);
+	if (b0 + 3u < wv.n_bins) c = *reinterpret_cast<const uint4*>(wv.bin_count + b0);
+	else { if (b0 < wv.n_bins) c.x = wv.bin_count[b0]; if (b0 + 1u < wv.n_bins) c.y = wv.bin_count[b0 + 1u]; if (b0 + 2u < wv.n_bins) c.z = wv.bin_count[b0 + 2u]; }
+	const uint32_t mine = c.x + c.y + c.z + c.w;
+	__syncthreads();
+	s_part[threadIdx.x] = mine;
+	__syncthreads();
+	for (uint32_t off = 1; off < BIN_SCAN_THREADS; off <<= 1) {
 		const uint32_t v = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0u;
 		__syncthreads();
 		s_part[threadIdx.x] += v;
 		__syncthreads();
 	}
-	uint32_t run = s_part[threadIdx.x] - sum;
-	for (uint32_t b = b0; b < b1; ++b) { const uint32_t c = wv.bin_count[b]; wv.bin_cursor[b] = run; wv.bin_count[b] = 0u; run += c; }
+	uint32_t run = s_before + s_part[threadIdx.x] - mine;
+	if (b0 < wv.n_bins) wv.bin_cursor[b0] = run; run += c.x;
+	if (b0 + 1u < wv.n_bins) wv.bin_cursor[b0 + 1u] = run; run += c.y;
+	if (b0 + 2u < wv.n_bins) wv.bin_cursor[b0 + 2u] = run; run += c.z;
+	if (b0 + 3u < wv.n_bins) wv.bin_cursor[b0 + 3u] = run;
 }
 
-__global__ void __launch_bounds__(STREAM_THREADS)
+__global__ void __launch_bounds__(BIN_THREADS)
 bin_permute_kernel(SceneView sv, WaveView wv, uint32_t bounce, int q_from) {
+	__shared__ uint32_t s_key[BIN_SLOTS], s_cnt[BIN_SLOTS], s_base[BIN_SLOTS];
 	if (bounce >= *wv.tail_from) return;
 	const uint32_t n = wv.n_live[bounce];
+	if (n == 0) return;
+	// the counters of this bounce are dead once bin_scan has run: leave them zero for the next binned bounce
+	for (uint32_t b = blockIdx.x * BIN_THREADS + threadIdx.x; b < wv.n_bins; b += gridDim.x * BIN_THREADS) wv.bin_count[b] = 0u;
 	const float4* __restrict__ ro = q_from ? wv.ray_o[1] : wv.ray_o[0];
 	const float4* __restrict__ rd = q_from ? wv.ray_d[1] : wv.ray_d[0];
 	const float4* __restrict__ rt_ = q_from ? wv.thr[1] : wv.thr[0];
 	float4* __restrict__ wo = q_from ? wv.ray_o[0] : wv.ray_o[1];
 	float4* __restrict__ wd = q_from ? wv.ray_d[0] : wv.ray_d[1];
 	float4* __restrict__ wt = q_from ? wv.thr[0] : wv.thr[1];
-	const uint32_t stride = gridDim.x * blockDim.x;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-		const float4 o = ldq(ro + i), d = ldq(rd + i), t = ldq(rt_ + i);
-		const uint32_t pos = warp_bin_add(wv.bin_cursor, wv.n_bins, ray_bin(sv, o, d));
-		RTB_CHECK(pos < n && pos < wv.capacity, RTB_BOUNDS_QUEUE);
-		wo[pos] = o; wd[pos] = d; wt[pos] = t;
+	for (uint32_t s = threadIdx.x; s < BIN_SLOTS; s += BIN_THREADS) { s_key[s] = BIN_EMPTY; s_cnt[s] = 0u; }
+	__syncthreads();
+	for (uint32_t base = blockIdx.x * BIN_TILE; base < n; base += gridDim.x * BIN_TILE) {
+		float4 o[BIN_ITEMS], d[BIN_ITEMS], t[BIN_ITEMS];
+		uint32_t slot[BIN_ITEMS];
+#pragma unroll
+		for (int k = 0; k < BIN_ITEMS; ++k) {
+			const uint32_t i = base + k * BIN_THREADS + threadIdx.x;
+			if (i < n) { o[k] = ldq(ro + i); d[k] = ldq(rd + i); t[k] = ldq(rt_ + i); }
+		}
+#pragma unroll
+		for (int k = 0; k < BIN_ITEMS; ++k) {
+			const uint32_t i = base + k * BIN_THREADS + threadIdx.x;
+			slot[k] = i < n ? bin_table_add(s_key, s_cnt, ray_bin(sv, o[k], d[k])) : 0u;
+		}
+		__syncthreads();
+		// a run of slots in the other queue for every distinct key of the tile
+		for (uint32_t s = threadIdx.x; s < BIN_SLOTS; s += BIN_THREADS) {
+			const uint32_t key = s_key[s];
+			if (key != BIN_EMPTY) { RTB_CHECK(key < wv.n_bins, RTB_BOUNDS_BIN); s_base[s] = atomicAdd(wv.bin_cursor + key, s_cnt[s]); s_cnt[s] = 0u; }
+		}
+		__syncthreads();
+#pragma unroll
+		for (int k = 0; k < BIN_ITEMS; ++k) {
+			const uint32_t i = base + k * BIN_THREADS + threadIdx.x;
+			if (i < n) {
+				const uint32_t pos = s_base[slot[k]] + atomicAdd(s_cnt + slot[k], 1u);
+				RTB_CHECK(pos < n && pos < wv.capacity, RTB_BOUNDS_QUEUE);
+				wo[pos] = o[k]; wd[pos] = d[k]; wt[pos] = t[k];
+			}
+		}
+		__syncthreads();
+		for (uint32_t s = threadIdx.x; s < BIN_SLOTS; s += BIN_THREADS) { s_key[s] = BIN_EMPTY; s_cnt[s] = 0u; }
+		__syncthreads();
 	}
 }
 
@@ -1208,6 +1295,9 @@ void query_occupancy(int device, LaunchCfg& lc) {
 	lc.blocks_traverse = sms * (occ_trav > 0 ? occ_trav : 1);
 	lc.blocks_shade = sms * (occ_s > 0 ? occ_s : 1);
 	lc.blocks_stream = sms * (occ_g > 0 ? occ_g : 1);
+	int occ_b = 0;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, bin_permute_kernel, BIN_THREADS, 0);
+	lc.blocks_bin = sms * (occ_b > 0 ? occ_b : 1);
 }
 
 void launch_generate(const BatchParams& bp, const rtb_camera& cam, const WaveView& wv, const LaunchCfg& lc, cudaStream_t st) {
@@ -1237,8 +1327,8 @@ void launch_tail(const SceneView& sv, const BatchParams& bp, const WaveView& wv,
 		else tail_kernel<false, STACK_SIZE><<<lc.blocks_tail, TRAVERSE_THREADS, 0, st>>>(sv, bp, wv, bounce, q, threshold);
 	}
 }
-void launch_shade(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, int q, int count_bins, const LaunchCfg& lc, cudaStream_t st) {
-	shade_kernel<<<lc.blocks_shade, SHADE_THREADS, 0, st>>>(sv, bp, wv, bounce, q, count_bins);
+void launch_shade(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, int q, const LaunchCfg& lc, cudaStream_t st) {
+	shade_kernel<<<lc.blocks_shade, SHADE_THREADS, 0, st>>>(sv, bp, wv, bounce, q);
 }
 void launch_texture(const SceneView& sv, const WaveView& wv, uint32_t bounce, int q_out, const LaunchCfg& lc, cudaStream_t st) {
 	const int blocks = lc.sms * 2 < lc.blocks_stream ? lc.sms * 2 : lc.blocks_stream;   // short work lists: a small grid keeps the launch cheap
@@ -1246,8 +1336,9 @@ void launch_texture(const SceneView& sv, const WaveView& wv, uint32_t bounce, in
 }
 void launch_bin_rays(const SceneView& sv, const WaveView& wv, uint32_t bounce, int q_from, const LaunchCfg& lc, cudaStream_t st) {
 	const uint32_t nbins = 1u << (3 * sv.bin_org_bits + 2 * sv.bin_dir_bits);
-	bin_scan_kernel<<<1, BIN_SCAN_THREADS, 0, st>>>(wv, bounce, nbins);
-	bin_permute_kernel<<<lc.blocks_stream, STREAM_THREADS, 0, st>>>(sv, wv, bounce, q_from);
+	bin_count_kernel<<<lc.blocks_bin, BIN_THREADS, 0, st>>>(sv, wv, bounce, q_from);
+	bin_scan_kernel<<<(nbins + BIN_SCAN_PER_BLOCK - 1) / BIN_SCAN_PER_BLOCK, BIN_SCAN_THREADS, 0, st>>>(wv, bounce);
+	bin_permute_kernel<<<lc.blocks_bin, BIN_THREADS, 0, st>>>(sv, wv, bounce, q_from);
 }
 void launch_accumulate(const BatchParams& bp, const WaveView& wv, float4* accum, float4* accum2, const LaunchCfg& lc, cudaStream_t st) {
 	accumulate_kernel<<<lc.blocks_stream, STREAM_THREADS, 0, st>>>(bp, wv, accum, accum2);

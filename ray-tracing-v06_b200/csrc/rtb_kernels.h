@@ -67,18 +67,18 @@ struct WaveView {
 	unsigned long long* totals; // [0] paths, [1] rays
 };
 
-struct LaunchCfg { int blocks_traverse, blocks_shade, blocks_stream, blocks_tail, sms; };
+struct LaunchCfg { int blocks_traverse, blocks_shade, blocks_stream, blocks_tail, blocks_bin, sms; };
 
 void launch_generate(const BatchParams& bp, const rtb_camera& cam, const WaveView& wv, const LaunchCfg& lc, cudaStream_t st);
 // `q` = which of the two ray queues holds the rays of `bounce` (the renderer's static schedule: the queues alternate from
 // bounce to bounce, except that a binned bounce is permuted back into the queue its predecessor was read from).
 void launch_traverse(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, int q, const LaunchCfg& lc, cudaStream_t st);
 void launch_tail(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, int q, uint32_t threshold, const LaunchCfg& lc, cudaStream_t st);
-// shade reads queue q and writes the survivors to queue q ^ 1; with count_bins it also counts them per bin (bin_count)
-void launch_shade(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, int q, int count_bins, const LaunchCfg& lc, cudaStream_t st);
+// shade reads queue q and writes the survivors to queue q ^ 1
+void launch_shade(const SceneView& sv, const BatchParams& bp, const WaveView& wv, uint32_t bounce, int q, const LaunchCfg& lc, cudaStream_t st);
 void launch_texture(const SceneView& sv, const WaveView& wv, uint32_t bounce, int q_out, const LaunchCfg& lc, cudaStream_t st);
-// Binning of the rays of `bounce` (counted by the shade launch before): prefix sums of the bin counts, then every ray of
-// queue q_from moves to its bin's range in queue q_from ^ 1.
+// Binning of the rays of `bounce` (a counting sort by ray_bin: count, prefix sums, permute): every ray of queue q_from
+// moves to its bin's range in queue q_from ^ 1.
 void launch_bin_rays(const SceneView& sv, const WaveView& wv, uint32_t bounce, int q_from, const LaunchCfg& lc, cudaStream_t st);
 void launch_accumulate(const BatchParams& bp, const WaveView& wv, float4* accum, float4* accum2, const LaunchCfg& lc, cudaStream_t st);
 void launch_resolve(const float4* accum, float4* out, uint32_t n, cudaStream_t st);

@@ -302,7 +302,7 @@ static void enqueue_batch(rtb_renderer* r, const BatchParams& bp, cudaStream_t s
 		if (r->tail_threshold && tail_checkpoint(b)) { prof_begin(r, 4, st); launch_tail(r->sv, bp, r->wv, b, q, r->tail_threshold, r->lc, st); prof_end(r, st); }
 		prof_begin(r, 1, st); launch_traverse(r->sv, bp, r->wv, b, q, r->lc, st); prof_end(r, st);
 		const bool bin_next = b + 1 < bp.max_depth && binned_bounce(r, b + 1);
-		prof_begin(r, 2, st); launch_shade(r->sv, bp, r->wv, b, q, bin_next ? 1 : 0, r->lc, st);
+		prof_begin(r, 2, st); launch_shade(r->sv, bp, r->wv, b, q, r->lc, st);
 		if (r->sv.has_deferred_tex && b + 1 < bp.max_depth) launch_texture(r->sv, r->wv, b, q ^ 1, r->lc, st);
 		prof_end(r, st);
 		if (bin_next) { prof_begin(r, 5, st); launch_bin_rays(r->sv, r->wv, b + 1, q ^ 1, r->lc, st); prof_end(r, st); }   // ... and back into queue q
@@ -367,7 +367,7 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 
 	const uint32_t n_batches = spp ? (uint32_t)((spp + S - 1) / S) : 0;
 	const uint64_t launches_per_batch = 3 + 2ull * bp.max_depth + (r->tail_threshold ? count_tail_checkpoints(bp.max_depth) : 0) +
-	                                    (r->sv.has_deferred_tex ? bp.max_depth - 1 : 0) + 2ull * count_binned_bounces(r, bp.max_depth);
+	                                    (r->sv.has_deferred_tex ? bp.max_depth - 1 : 0) + 3ull * count_binned_bounces(r, bp.max_depth);
 	const bool use_graph = getenv("RTB_NO_GRAPH") == nullptr && n_batches > 0 && !r->profiling;
 	if (use_graph) {
 		bool reuse = r->graph_valid && memcmp(&r->graph_bp, &bp, sizeof bp) == 0 && memcmp(&r->graph_cam, &r->cam, sizeof r->cam) == 0 &&
@@ -557,7 +557,7 @@ int rtb_get_profile(rtb_renderer* r, rtb_profile* out) {
 	}
 	out->generate_ms = ms[0]; out->traverse_ms = ms[1]; out->shade_ms = ms[2]; out->accumulate_ms = ms[3];
 	out->tail_ms = ms[4]; out->tail_launches = cnt[4];
-	out->bin_ms = ms[5]; out->bin_launches = 2 * cnt[5];
+	out->bin_ms = ms[5]; out->bin_launches = 3 * cnt[5];
 	out->generate_launches = cnt[0]; out->traverse_launches = cnt[1]; out->shade_launches = cnt[2]; out->accumulate_launches = 2 * cnt[3];
 	r->prof_used = 0;
 	return RTB_OK;

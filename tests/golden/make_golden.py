@@ -26,6 +26,9 @@ Fixtures:
   ref_sphere_index_host_1280x720.npz       (`python tests/golden/make_golden.py sphere_index`, CPU) the ground truth of the reference's
                                            own unit test (google_testing/test.cpp:87-106) computed by the reference's
                                            _sphere_closest_intersection + PinholeCamera (oracle/_ref/ref_sphere_index host)
+  book2_final.rtbs / .json                 (`python tests/golden/make_golden.py scenes`) the headline scene serialised by the host mirror
+                                           (RTBS blob, camera as hex floats, sizes): what `bench.py --impl reference` renders, so
+                                           that arm loads nothing of the product
   ref_bvh_book2_bouncing.bin               node array + primitive order of the reference's BuildBVH_TopDown
   oracle_images_32x18.npz                  (`python tests/golden/make_golden.py oracle`) the ORACLE's own Philox renders of every
                                            registered scene at 32x18, 2 spp, depth 8 - not a reference fixture: a tripwire that
@@ -68,6 +71,20 @@ def bvh():
     print("wrote", GOLD / "ref_bvh_book2_bouncing.bin")
 
 
+def scenes():
+    """The headline scene as the oracle-side fixture of bench.py --impl reference: RTBS blob + camera + sizes."""
+    import json
+    rtb = importlib.import_module("ray-tracing-v06_b200")
+    sys.path.insert(0, str(ROOT / "oracle")); orc = importlib.import_module("pyoracle")
+    for name in ("book2_final",):
+        s = rtb.Scene.named(name)
+        (GOLD / f"{name}.rtbs").write_bytes(s.serialize())
+        meta = {"scene": name, "width": int(s.info.width), "height": int(s.info.height), "spp": int(s.info.spp), "max_depth": int(s.info.max_depth),
+                "camera": orc.camera_to_dict(s.info.camera)}
+        (GOLD / f"{name}.json").write_text(json.dumps(meta, indent=1) + "\n")
+        print("wrote", GOLD / f"{name}.rtbs", (GOLD / f"{name}.rtbs").stat().st_size, "bytes")
+
+
 def sphere_index():
     rtb = importlib.import_module("ray-tracing-v06_b200")
     sys.path.insert(0, str(ROOT / "tests")); import helpers
@@ -102,4 +119,4 @@ def collect():
 
 
 if __name__ == "__main__":
-    {"bvh": bvh, "collect": collect, "oracle": oracle_images, "trace_rays": trace_rays, "sphere_index": sphere_index, "collect_trace": collect_trace}[sys.argv[1]]()
+    {"bvh": bvh, "collect": collect, "oracle": oracle_images, "trace_rays": trace_rays, "sphere_index": sphere_index, "scenes": scenes, "collect_trace": collect_trace}[sys.argv[1]]()

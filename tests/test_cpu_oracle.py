@@ -301,3 +301,18 @@ def test_analytic_checker_truncation(rtb, orc):
 def test_analytic_image_texture(rtb, orc):
     import analytic
     analytic.check_image_texture_lookup(rtb, _oracle_render(orc))
+
+
+def test_committed_headline_scene_is_current(rtb, orc):
+    """tests/golden/book2_final.rtbs + .json (what `bench.py --impl reference` renders without touching the product) is
+    what the host mirror builds today, byte for byte, camera included."""
+    import json
+    s = rtb.Scene.named("book2_final")
+    assert (GOLDEN / "book2_final.rtbs").read_bytes() == s.serialize()
+    meta = json.loads((GOLDEN / "book2_final.json").read_text())
+    assert (meta["width"], meta["height"], meta["max_depth"]) == (s.info.width, s.info.height, s.info.max_depth)
+    cam = orc.camera_from_dict(meta["camera"])
+    assert bytes(cam) == bytes(s.info.camera)
+    a, _, ra = orc.OracleScene((GOLDEN / "book2_final.rtbs").read_bytes()).render(cam, 24, 24, 0, 2, 12, seed=3)
+    b, _, rb = orc.OracleScene(s.serialize()).render(s.info.camera, 24, 24, 0, 2, 12, seed=3)
+    assert np.array_equal(a, b) and ra == rb

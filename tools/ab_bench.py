@@ -33,9 +33,9 @@ if __name__ == "__main__":
     rows = []
     for name in sys.argv[1:]:
         env = {}
-        if "@" in name:                         # name@VAR=value,VAR2=value2 : same library, different environment
+        if "@" in name:                         # name@VAR=value;VAR2=value2 : same library, different environment
             name, kv = name.split("@", 1)
-            env = dict(x.split("=", 1) for x in kv.split(","))
+            env = dict(x.split("=", 1) for x in kv.split(";"))
         r = run(name, extra_env=env); r["env"] = env
         rows.append(r)
         print(json.dumps(r), flush=True)

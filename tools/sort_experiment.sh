@@ -1,7 +1,8 @@
 #!/bin/bash
-# Traverse time per bounce on a globally re-sorted queue (RTB_SORT_EXPERIMENT=<mode>,<hex mask of bounces>, csrc/rtb_sort.cu).
-# mode = org_bits << 4 | dir_bits (| 0x100: direction-major)
+# Traverse time per bounce on a globally re-sorted queue (RTB_SORT_EXPERIMENT=<mode>,<hex mask of bounces>, csrc/rtb_sort.cu),
+# production binning switched off.  mode = org_bits << 4 | dir_bits (| 0x100: direction-major)
 cd "$(dirname "$0")/.."
+export RTB_BIN_BITS=0,0
 for spec in "$@"; do
   RTB_SORT_EXPERIMENT=$spec python tools/bounce_profile.py > gpurun_out/sort_tmp.json 2>> gpurun_out/sort.err
   python - <<PY
