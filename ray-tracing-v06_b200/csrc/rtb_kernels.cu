@@ -91,6 +91,18 @@ __device__ __forceinline__ void stq(float4* p, float4 v) { *p = v; }
 __device__ __forceinline__ void stq(int2* p, int2 v) { *p = v; }
 #endif
 
+// A ray record is 32 bytes, 32-byte aligned: one 256-bit access (LDG / STG.E.256 of sm_100) moves it, so a warp reading or
+// writing 32 consecutive records touches 1 KB exactly once (two 128-bit accesses at a 32-byte stride ask L1 for every
+// sector twice: shade measured 9 % slower that way).
+__device__ __forceinline__ void ld_ray(const float4* rec, float4& o, float4& d) {
+	asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w), "=f"(d.x), "=f"(d.y), "=f"(d.z), "=f"(d.w) : "l"(rec));
+}
+__device__ __forceinline__ void st_ray(float4* rec, const float4& o, const float4& d) {
+	asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+	             :: "l"(rec), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w) : "memory");
+}
+
 // Path id -> (global pixel index, absolute sample index).  Paths of a batch are laid out
 // sample-major: id = local_sample * npix + local_pixel, local pixels row-major from row_begin.
 __device__ __forceinline__ void path_pixel_sample(const BatchParams& bp, uint32_t batch, uint32_t path,
@@ -157,8 +169,7 @@ generate_kernel(BatchParams bp, rtb_camera cam, WaveView wv) {
 			d = rt::madd(cv, t, rt::madd(cu, s, cw));
 			if (cam.kind == RTB_CAM_MOTION) time = rt::mixf(cam.t0, cam.t1, r.z);
 		}
-		stq(wv.ray_o[0] + path, make_float4(o.x, o.y, o.z, time));
-		stq(wv.ray_d[0] + path, make_float4(d.x, d.y, d.z, __uint_as_float(path)));
+		st_ray(wv.ray_od[0] + 2 * (size_t)path, make_float4(o.x, o.y, o.z, time), make_float4(d.x, d.y, d.z, __uint_as_float(path)));
 		stq(wv.thr[0] + path, make_float4(1.0f, 1.0f, 1.0f, 0.0f));
 		stq(wv.contrib + path, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
 	}
@@ -579,8 +590,7 @@ traverse_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce, int 
 	if (blockIdx.x == 0 && threadIdx.x == 0) { RTB_COUNT_CHECKS(n); RTB_CHECK(n <= wv.capacity, RTB_BOUNDS_QUEUE); }
 	const uint32_t batch = *wv.batch_index;
 	const int lane = threadIdx.x & 31;
-	const float4* __restrict__ ro = q ? wv.ray_o[1] : wv.ray_o[0];
-	const float4* __restrict__ rd = q ? wv.ray_d[1] : wv.ray_d[0];
+	const float4* __restrict__ rod = q ? wv.ray_od[1] : wv.ray_od[0];
 	uint32_t* counter = wv.work + 2 * bounce;
 	// Every warp owns one static chunk of 32 rays; only when the queue is longer than the whole
 	// grid do warps pull further chunks from the device counter (short queues cost no atomics).
@@ -590,7 +600,7 @@ traverse_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce, int 
 	while (base < n) {
 		const uint32_t i = base + lane;
 		if (i < n) {
-			const float4 fo = ldq(ro + i), fd = ldq(rd + i);
+			float4 fo, fd; ld_ray(rod + 2 * (size_t)i, fo, fd);
 			MediumRng mr = make_medium_rng(bp, batch, __float_as_uint(fd.w), bounce);
 			float t; int code;
 			trace_ray<MEDIA>(sv, xyz(fo), xyz(fd), fo.w, mr, s_stack + threadIdx.x, STACK, t, code);
@@ -868,7 +878,36 @@ __device__ __forceinline__ uint32_t ray_bin(const SceneView& sv, const float4& o
 	}
 	return key;
 }
-__global__ void __launch_bounds__(SHADE_THREADS)
+// Shared-memory hash table of (bin, rays) used by the binning kernels (see "binning" below).
+#define BIN_THREADS 256
+#define BIN_ITEMS 4                                  // rays per thread per tile
+#define BIN_TILE (BIN_THREADS * BIN_ITEMS)
+#define BIN_SLOTS 2048                               // hash slots per block: at most half full with one tile's keys
+#define BIN_EMPTY 0xFFFFFFFFu
+
+// Finds or claims the slot of `key` and counts one ray in it (linear probing; callers keep the table at most half full).
+// Returns the slot, with the top bit set when this call claimed it.
+__device__ __forceinline__ uint32_t bin_table_add(uint32_t* s_key, uint32_t* s_cnt, uint32_t key) {
+	uint32_t h = (key * 2654435761u) >> (32 - 11);  // Fibonacci hash to log2(BIN_SLOTS) = 11 bits
+	for (;;) {
+		const uint32_t prev = atomicCAS(s_key + h, BIN_EMPTY, key);
+		if (prev == BIN_EMPTY || prev == key) { atomicAdd(s_cnt + h, 1u); return prev == BIN_EMPTY ? (h | 0x80000000u) : h; }
+		h = (h + 1u) & (BIN_SLOTS - 1u);
+	}
+}
+
+// One global atomic per bin the table holds, then the table is empty again (all threads of the block).
+__device__ __forceinline__ void bin_table_flush(uint32_t* s_key, uint32_t* s_cnt, uint32_t* bin_count, uint32_t n_bins, int threads) {
+	for (uint32_t s = threadIdx.x; s < BIN_SLOTS; s += threads) {
+		const uint32_t key = s_key[s];
+		if (key != BIN_EMPTY) { RTB_CHECK(key < n_bins, RTB_BOUNDS_BIN); atomicAdd(bin_count + key, s_cnt[s]); s_key[s] = BIN_EMPTY; s_cnt[s] = 0u; }
+	}
+}
+
+#ifndef SHADE_MIN_BLOCKS
+#define SHADE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS)
 shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce, int q) {
 	__shared__ uint32_t s_chunk, s_base;
 	__shared__ uint32_t s_warp[SHADE_THREADS / 32];
@@ -878,13 +917,12 @@ shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce, int q) 
 	const uint32_t batch = *wv.batch_index;
 	const int in = q, out = in ^ 1;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const float4* __restrict__ ro = in ? wv.ray_o[1] : wv.ray_o[0];
-	const float4* __restrict__ rd = in ? wv.ray_d[1] : wv.ray_d[0];
+	const float4* __restrict__ rod = in ? wv.ray_od[1] : wv.ray_od[0];
 	const float4* __restrict__ rt_ = in ? wv.thr[1] : wv.thr[0];
-	float4* __restrict__ wo = out ? wv.ray_o[1] : wv.ray_o[0];
-	float4* __restrict__ wd = out ? wv.ray_d[1] : wv.ray_d[0];
+	float4* __restrict__ wod = out ? wv.ray_od[1] : wv.ray_od[0];
 	float4* __restrict__ wt = out ? wv.thr[1] : wv.thr[0];
 	uint32_t* counter = wv.work + 2 * bounce + 1;
+
 	// the first chunk of every block is static; further chunks come from the device counter
 	uint32_t base = blockIdx.x * SHADE_THREADS;
 	const uint32_t static_span = gridDim.x * SHADE_THREADS;
@@ -895,7 +933,8 @@ shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce, int q) 
 		float4 no = make_float4(0, 0, 0, 0), nd = no; v3 nthr = rt::mk(0, 0, 0);
 		DeferredTex dt; dt.tex = -1; dt.u = dt.v = 0.0f; dt.p = rt::mk(0, 0, 0);
 		if (i < n) {
-			const float4 fo = ldq(ro + i), fd = ldq(rd + i), ft = ldq(rt_ + i);
+			float4 fo, fd; ld_ray(rod + 2 * (size_t)i, fo, fd);
+			const float4 ft = ldq(rt_ + i);
 			const int2 h = ldq(wv.hit + i);
 			alive = shade_segment<true>(sv, bp, wv, batch, bounce, fo, fd, xyz(ft), __int_as_float(h.x), h.y, no, nd, nthr, dt);
 		}
@@ -914,7 +953,7 @@ shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce, int q) 
 		if (alive) {
 			const uint32_t pos = s_base + s_warp[warp] + __popc(mask & ((1u << lane) - 1u));
 			RTB_CHECK(pos < wv.capacity && pos < n, RTB_BOUNDS_QUEUE);
-			stq(wo + pos, no); stq(wd + pos, nd); stq(wt + pos, make_float4(nthr.x, nthr.y, nthr.z, 0.0f));
+			st_ray(wod + 2 * (size_t)pos, no, nd); stq(wt + pos, make_float4(nthr.x, nthr.y, nthr.z, 0.0f));
 			// texture work list: (p, queue slot), (u, v, -, texture id)
 			const bool defer = dt.tex >= 0;
 			const uint32_t act = __activemask();
@@ -969,46 +1008,36 @@ texture_kernel(SceneView sv, WaveView wv, uint32_t bounce, int q_out) {
 // key.  Where a ray sits in a queue changes nothing about the image - contributions are stored by path id and summed per
 // pixel in sample order - only which rays share a warp.
 
-#define BIN_THREADS 256
-#define BIN_ITEMS 4                                  // rays per thread per tile
-#define BIN_TILE (BIN_THREADS * BIN_ITEMS)
-#define BIN_SLOTS 2048                               // hash slots per block: at most half full with one tile's keys
-#define BIN_EMPTY 0xFFFFFFFFu
-
-// Finds or claims the slot of `key` and counts one ray in it (linear probing; the table never fills: <= BIN_TILE keys).
-__device__ __forceinline__ uint32_t bin_table_add(uint32_t* s_key, uint32_t* s_cnt, uint32_t key) {
-	uint32_t h = (key * 2654435761u) >> (32 - 11);  // Fibonacci hash to log2(BIN_SLOTS) = 11 bits
-	for (;;) {
-		const uint32_t prev = atomicCAS(s_key + h, BIN_EMPTY, key);
-		if (prev == BIN_EMPTY || prev == key) { atomicAdd(s_cnt + h, 1u); return h; }
-		h = (h + 1u) & (BIN_SLOTS - 1u);
-	}
-}
-
+// Rays per bin.  A block's counts gather in its table over many tiles and go to the global counters when the table might
+// not hold another tile's keys, and at the end.
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_count_kernel(SceneView sv, WaveView wv, uint32_t bounce, int q) {
 	__shared__ uint32_t s_key[BIN_SLOTS], s_cnt[BIN_SLOTS];
+	__shared__ uint32_t s_used;
 	if (bounce >= *wv.tail_from) return;
 	const uint32_t n = wv.n_live[bounce];
 	if (n == 0) return;
-	const float4* __restrict__ ro = q ? wv.ray_o[1] : wv.ray_o[0];
-	const float4* __restrict__ rd = q ? wv.ray_d[1] : wv.ray_d[0];
+	const float4* __restrict__ rod = q ? wv.ray_od[1] : wv.ray_od[0];
 	for (uint32_t s = threadIdx.x; s < BIN_SLOTS; s += BIN_THREADS) { s_key[s] = BIN_EMPTY; s_cnt[s] = 0u; }
+	if (threadIdx.x == 0) s_used = 0u;
 	__syncthreads();
 	for (uint32_t base = blockIdx.x * BIN_TILE; base < n; base += gridDim.x * BIN_TILE) {
+		uint32_t claimed = 0;
 #pragma unroll
 		for (int k = 0; k < BIN_ITEMS; ++k) {
 			const uint32_t i = base + k * BIN_THREADS + threadIdx.x;
-			if (i < n) bin_table_add(s_key, s_cnt, ray_bin(sv, ldq(ro + i), ldq(rd + i)));
+			if (i < n) { float4 o, d; ld_ray(rod + 2 * (size_t)i, o, d); claimed += bin_table_add(s_key, s_cnt, ray_bin(sv, o, d)) >> 31; }
 		}
+		if (claimed) atomicAdd(&s_used, claimed);
 		__syncthreads();
-		// one global atomic per distinct key of the tile, then the table is empty again
-		for (uint32_t s = threadIdx.x; s < BIN_SLOTS; s += BIN_THREADS) {
-			const uint32_t key = s_key[s];
-			if (key != BIN_EMPTY) { RTB_CHECK(key < wv.n_bins, RTB_BOUNDS_BIN); atomicAdd(wv.bin_count + key, s_cnt[s]); s_key[s] = BIN_EMPTY; s_cnt[s] = 0u; }
+		if (s_used > BIN_SLOTS / 2 - BIN_TILE / 2) {          // (a tile adds at most BIN_TILE keys; past this mark, flush)
+			__syncthreads();
+			bin_table_flush(s_key, s_cnt, wv.bin_count, wv.n_bins, BIN_THREADS);
+			if (threadIdx.x == 0) s_used = 0u;
+			__syncthreads();
 		}
-		__syncthreads();
 	}
+	bin_table_flush(s_key, s_cnt, wv.bin_count, wv.n_bins, BIN_THREADS);
 }
 
 // Block b owns bins [b * 4096, (b + 1) * 4096): it adds up everything before them (the counts are re-read from L2 - at
@@ -1061,11 +1090,9 @@ bin_permute_kernel(SceneView sv, WaveView wv, uint32_t bounce, int q_from) {
 	if (n == 0) return;
 	// the counters of this bounce are dead once bin_scan has run: leave them zero for the next binned bounce
 	for (uint32_t b = blockIdx.x * BIN_THREADS + threadIdx.x; b < wv.n_bins; b += gridDim.x * BIN_THREADS) wv.bin_count[b] = 0u;
-	const float4* __restrict__ ro = q_from ? wv.ray_o[1] : wv.ray_o[0];
-	const float4* __restrict__ rd = q_from ? wv.ray_d[1] : wv.ray_d[0];
+	const float4* __restrict__ rod = q_from ? wv.ray_od[1] : wv.ray_od[0];
 	const float4* __restrict__ rt_ = q_from ? wv.thr[1] : wv.thr[0];
-	float4* __restrict__ wo = q_from ? wv.ray_o[0] : wv.ray_o[1];
-	float4* __restrict__ wd = q_from ? wv.ray_d[0] : wv.ray_d[1];
+	float4* __restrict__ wod = q_from ? wv.ray_od[0] : wv.ray_od[1];
 	float4* __restrict__ wt = q_from ? wv.thr[0] : wv.thr[1];
 	for (uint32_t s = threadIdx.x; s < BIN_SLOTS; s += BIN_THREADS) { s_key[s] = BIN_EMPTY; s_cnt[s] = 0u; }
 	__syncthreads();
@@ -1075,12 +1102,12 @@ bin_permute_kernel(SceneView sv, WaveView wv, uint32_t bounce, int q_from) {
 #pragma unroll
 		for (int k = 0; k < BIN_ITEMS; ++k) {
 			const uint32_t i = base + k * BIN_THREADS + threadIdx.x;
-			if (i < n) { o[k] = ldq(ro + i); d[k] = ldq(rd + i); t[k] = ldq(rt_ + i); }
+			if (i < n) { ld_ray(rod + 2 * (size_t)i, o[k], d[k]); t[k] = ldq(rt_ + i); }
 		}
 #pragma unroll
 		for (int k = 0; k < BIN_ITEMS; ++k) {
 			const uint32_t i = base + k * BIN_THREADS + threadIdx.x;
-			slot[k] = i < n ? bin_table_add(s_key, s_cnt, ray_bin(sv, o[k], d[k])) : 0u;
+			slot[k] = i < n ? (bin_table_add(s_key, s_cnt, ray_bin(sv, o[k], d[k])) & 0x7FFFFFFFu) : 0u;
 		}
 		__syncthreads();
 		// a run of slots in the other queue for every distinct key of the tile
@@ -1095,7 +1122,7 @@ bin_permute_kernel(SceneView sv, WaveView wv, uint32_t bounce, int q_from) {
 			if (i < n) {
 				const uint32_t pos = s_base[slot[k]] + atomicAdd(s_cnt + slot[k], 1u);
 				RTB_CHECK(pos < n && pos < wv.capacity, RTB_BOUNDS_QUEUE);
-				wo[pos] = o[k]; wd[pos] = d[k]; wt[pos] = t[k];
+				st_ray(wod + 2 * (size_t)pos, o[k], d[k]); wt[pos] = t[k];   // (the 32-byte ray record is one whole sector)
 			}
 		}
 		__syncthreads();
@@ -1119,13 +1146,12 @@ tail_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce0, int q, 
 	if (blockIdx.x == 0 && threadIdx.x == 0) *wv.tail_from = bounce0;
 	const uint32_t batch = *wv.batch_index;
 	const int in = q;
-	const float4* __restrict__ ro = in ? wv.ray_o[1] : wv.ray_o[0];
-	const float4* __restrict__ rd = in ? wv.ray_d[1] : wv.ray_d[0];
+	const float4* __restrict__ rod = in ? wv.ray_od[1] : wv.ray_od[0];
 	const float4* __restrict__ rt_ = in ? wv.thr[1] : wv.thr[0];
 	unsigned long long extra = 0;
 	const uint32_t stride = gridDim.x * blockDim.x;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-		float4 fo = ro[i], fd = rd[i];
+		float4 fo, fd; ld_ray(rod + 2 * (size_t)i, fo, fd);
 		v3 thr = xyz(rt_[i]);
 		MediumRng mr = make_medium_rng(bp, batch, __float_as_uint(fd.w), bounce0);
 		for (uint32_t b = bounce0; b < bp.max_depth; ++b) {

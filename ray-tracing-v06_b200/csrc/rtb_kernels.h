@@ -47,10 +47,10 @@ struct BatchParams {
 	uint32_t variance;
 };
 
-// Wavefront queues, structure-of-arrays, double buffered by bounce parity.
+// Wavefront queues, double buffered.  A ray is a 32-byte record (o.xyz, time)(d.xyz, path id bits) - one DRAM sector, so
+// the binning pass, which scatters rays, writes whole sectors - plus its throughput in a parallel array.
 struct WaveView {
-	float4* ray_o[2];           // (o.xyz, time)
-	float4* ray_d[2];           // (d.xyz, path id bits)
+	float4* ray_od[2];          // 2 x float4 per ray: (o.xyz, time), (d.xyz, path id bits)
 	float4* thr[2];             // (throughput rgb, -)
 	int2* hit;                  // (t bits, leaf code or -1)
 	float4* contrib;            // per path: radiance carried by the terminated path

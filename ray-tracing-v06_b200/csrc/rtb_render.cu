@@ -251,7 +251,7 @@ static int ensure_wave(rtb_renderer* r, size_t paths, uint32_t depth) {
 	size_t P = align_up(paths, 256);
 	size_t off = 0;
 	auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-	size_t o_ro0 = take(P * 16), o_ro1 = take(P * 16), o_rd0 = take(P * 16), o_rd1 = take(P * 16);
+	size_t o_od0 = take(P * 32), o_od1 = take(P * 32);
 	size_t o_t0 = take(P * 16), o_t1 = take(P * 16), o_hit = take(P * 8), o_con = take(P * 16);
 	size_t o_live = take((depth + 2) * 4), o_work = take(2 * (depth + 2) * 4), o_batch = take(256), o_tot = take(256);
 	size_t o_tex = take(P * 32), o_ntex = take((depth + 2) * 4);
@@ -260,8 +260,7 @@ static int ensure_wave(rtb_renderer* r, size_t paths, uint32_t depth) {
 	CUDA_TRY(cudaMalloc(&r->d_wave, off));
 	CUDA_TRY(cudaMemset(r->d_wave, 0, off));
 	uint8_t* b = static_cast<uint8_t*>(r->d_wave);
-	r->wv.ray_o[0] = (float4*)(b + o_ro0); r->wv.ray_o[1] = (float4*)(b + o_ro1);
-	r->wv.ray_d[0] = (float4*)(b + o_rd0); r->wv.ray_d[1] = (float4*)(b + o_rd1);
+	r->wv.ray_od[0] = (float4*)(b + o_od0); r->wv.ray_od[1] = (float4*)(b + o_od1);
 	r->wv.thr[0] = (float4*)(b + o_t0); r->wv.thr[1] = (float4*)(b + o_t1);
 	r->wv.hit = (int2*)(b + o_hit); r->wv.contrib = (float4*)(b + o_con);
 	r->wv.n_live = (uint32_t*)(b + o_live); r->wv.work = (uint32_t*)(b + o_work);
@@ -293,12 +292,8 @@ static uint32_t count_binned_bounces(const rtb_renderer* r, uint32_t depth) { ui
 
 static void enqueue_batch(rtb_renderer* r, const BatchParams& bp, cudaStream_t st) {
 	prof_begin(r, 0, st); launch_generate(bp, r->cam, r->wv, r->lc, st); prof_end(r, st);
-	// EXPERIMENT (profiling renders only, rtb_sort.cu): RTB_SORT_EXPERIMENT=<mode>,<hex mask of bounces>
-	int sort_mode = 0; unsigned long long sort_mask = 0x1FEull;
-	if (r->profiling) if (const char* e = getenv("RTB_SORT_EXPERIMENT")) { unsigned m = 0; unsigned long long k2 = 0; int k = sscanf(e, "%u,%llx", &m, &k2); if (k >= 1) sort_mode = (int)m; if (k >= 2) sort_mask = k2; }
 	int q = 0;   // the queue that holds the rays of bounce b
 	for (uint32_t b = 0; b < bp.max_depth; ++b) {
-		if (sort_mode && b < 64 && ((sort_mask >> b) & 1ull)) experimental_sort_queue(r, b, q, sort_mode, r->world_min, r->world_max);
 		if (r->tail_threshold && tail_checkpoint(b)) { prof_begin(r, 4, st); launch_tail(r->sv, bp, r->wv, b, q, r->tail_threshold, r->lc, st); prof_end(r, st); }
 		prof_begin(r, 1, st); launch_traverse(r->sv, bp, r->wv, b, q, r->lc, st); prof_end(r, st);
 		const bool bin_next = b + 1 < bp.max_depth && binned_bounce(r, b + 1);

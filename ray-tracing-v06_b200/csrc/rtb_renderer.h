@@ -73,7 +73,6 @@ struct rtb_renderer {
 // Resolve (mean -> clamp -> sqrt) of an arbitrary accumulator on this renderer's device and stream (rtb_multi.cu resolves
 // the cross-device total with it).
 int rtb_resolve_from(rtb_renderer* r, const float4* accum, void* d_out, void* user_stream);
-namespace rtb { int experimental_sort_queue(rtb_renderer* r, uint32_t bounce, int q, int mode, const float* world_min, const float* world_max); }   // rtb_sort.cu
 int rtb_quantize_from(rtb_renderer* r, const float4* accum, uint8_t* host_rgb, int flip_rows);
 
 #endif
