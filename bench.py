@@ -4,12 +4,12 @@
     python bench.py --gpus N --steps K --warmup W            # the B200 wavefront path tracer
     python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference on the host cores
 
-A "step" is one pass of the hot path over one batch of synthetic input: `--spp-per-step` samples of
-every pixel of the 800x800 Book 2 final scene, depth 40, per GPU (weak scaling: each rank renders its
-own sample range of the same frame — the sample-range partition of the 10,000 spp job — and the
-per-rank radiance sums are summed onto rank 0 with one NCCL reduce per step).  Rank 0 prints ONE JSON
-line.  `value` is Mrays/s (ray segments submitted to closest-hit traversal per second, all ranks);
-Mpaths/s rides along in `paths`.
+A "step" is one pass of the hot path over one batch of synthetic input: `--spp-per-step` samples (800 by
+default) of every pixel of the 800x800 Book 2 final scene, depth 40 - a FIXED total, split over the N ranks
+by sample range (strong scaling: rank r renders samples [r S/N, (r+1) S/N) of the step, exactly the
+partition of the 10,000 spp job), and the per-rank radiance sums are summed onto rank 0 with one NCCL
+reduce per step.  Rank 0 prints ONE JSON line.  `value` is Mrays/s (ray segments submitted to closest-hit
+traversal per second, all ranks); Mpaths/s rides along in `paths`.
 
 The oracle (oracle/) is used here only as the checker / CPU baseline, never as the thing measured in
 the default arm.
@@ -95,34 +95,39 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def load_golden_scene():
+    """The headline scene as a committed RTBS blob + camera (tests/golden/book2_final.rtbs, .json - written by
+    tests/golden/make_golden.py scenes): the reference arm maps only oracle/, never the product's libraries."""
+    orc = importlib.import_module("pyoracle")
+    blob = (ROOT / "tests" / "golden" / f"{SCENE}.rtbs").read_bytes()
+    meta = json.loads((ROOT / "tests" / "golden" / f"{SCENE}.json").read_text())
+    return orc, orc.OracleScene(blob), orc.camera_from_dict(meta["camera"]), meta
+
+
 def run_reference_arm(args, rank, world):
     """The reference's own implementation of the path on the host cores.  The reference has no CPU
     renderer (its integrator is __device__-only), so this is the CPU restatement of it (oracle/, kind
     "port") on all host threads, on a bounded sample of the same workload."""
     if rank != 0:
         return
-    pkg = importlib.import_module("ray-tracing-v06_b200")
-    orc = importlib.import_module("pyoracle")
-    scene = pkg.Scene.named(SCENE)
-    info = scene.info
-    o = orc.OracleScene(scene.serialize())
+    orc, o, cam, meta = load_golden_scene()
     threads = os.cpu_count() or 1
-    W, H, depth = info.width, info.height, info.max_depth
+    W, H, depth = meta["width"], meta["height"], meta["max_depth"]
     spp = args.ref_spp
     for i in range(args.warmup):
-        o.render(info.camera, W, H, i * spp, (i + 1) * spp, depth, seed=1984, threads=threads)
+        o.render(cam, W, H, i * spp, (i + 1) * spp, depth, seed=1984, threads=threads)
     t0 = time.perf_counter(); rays = 0
     for i in range(args.steps):
         s0 = (args.warmup + i) * spp
-        _, _, r = o.render(info.camera, W, H, s0, s0 + spp, depth, seed=1984, threads=threads)
+        _, _, r = o.render(cam, W, H, s0, s0 + spp, depth, seed=1984, threads=threads)
         rays += r
     dt = time.perf_counter() - t0
     mrays = rays / dt / 1e6
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Book 2 final scene {W}x{H} depth {depth}, step = {spp} spp of every pixel (bounded sample of the 10000 spp job)",
-                   "scene": SCENE, "rng": "philox4x32-10 keyed (seed,pixel)x(sample,bounce,stream)"},
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"Book 2 final scene {W}x{H} depth {depth} (BASELINE.json configs[4]), step = {spp} spp of every pixel (bounded sample of the 10000 spp job; a rate, "
+                               f"so comparable with the GPU arm's {args.spp_per_step}-spp steps)", "scene": SCENE, "rng": "philox4x32-10 keyed (seed,pixel)x(sample,bounce,stream)"},
         "paths": {"value": W * H * spp * args.steps / dt / 1e6, "unit": "Mpaths/s"},
         "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps x {W}x{H}x{spp} spp, std::thread over image rows, -O2, no fast-math; the reference has no CPU renderer, this is oracle/ (CPU restatement)"},
@@ -130,6 +135,24 @@ def run_reference_arm(args, rank, world):
         "gpu_launches": 0,
     }
     print(json.dumps(line), file=_JSON_OUT, flush=True)
+
+
+def load_ncu_profile():
+    """Counters of the dominant kernel from the committed ncu capture (profiles/r2_ncu.json, written by
+    tools/ncu_summary.py json): nothing profiler-derived is typed into this script.  `stale` says the capture was taken
+    at another commit of the kernel sources."""
+    p = ROOT / "profiles" / "r2_ncu.json"
+    if not p.exists():
+        return None
+    j = json.loads(p.read_text())
+    try:
+        head = subprocess.run(["git", "-C", str(ROOT), "log", "-1", "--format=%H", "--", "ray-tracing-v06_b200/csrc"], capture_output=True, text=True, timeout=10).stdout.strip()
+    except Exception:
+        head = ""
+    j["stale"] = bool(head) and bool(j.get("kernel_sources_commit")) and head != j["kernel_sources_commit"]
+    if not head:
+        j["stale"] = None      # no git history on this box: cannot tell
+    return j
 
 
 _JSON_OUT = sys.stdout
@@ -154,7 +177,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--spp-per-step", type=int, default=100, help="samples per pixel per GPU per step")
+    ap.add_argument("--spp-per-step", type=int, default=800, help="samples per pixel per step, ALL GPUs together (split by sample range)")
     ap.add_argument("--cpu-spp", type=int, default=128, help="samples per pixel of the cpu_baseline sample (rank 0, N=1)")
     ap.add_argument("--ref-spp", type=int, default=16, help="samples per pixel per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -194,13 +217,15 @@ def main():
     scene = pkg.Scene.named(SCENE)
     info = scene.info
     W, H, depth, S = info.width, info.height, info.max_depth, args.spp_per_step
+    if S < world:
+        raise SystemExit("bench.py: --spp-per-step must be at least the number of GPUs")
     r = pkg.Renderer(local_rank)
     r.set_scene(scene); r.set_camera(info.camera)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step(i, clear=True):
-        s0 = (i * world + rank) * S              # this rank's sample range of the job
-        r.render(W, H, s0, s0 + S, depth, seed=1984, clear=clear, stream=stream)
+        a, b = pkg.sample_range(S, rank, world)   # this rank's share of the step's S samples (strong scaling)
+        r.render(W, H, i * S + a, i * S + b, depth, seed=1984, clear=clear, stream=stream)
         if world > 1:
             dist.reduce(r.accum_tensor(), dst=0)  # the only collective: framebuffer sum over NVLink
 
@@ -236,9 +261,12 @@ def main():
     e2e_steps = max(1, min(args.steps, 5))
     r.set_scene(scene); step(0); r.download_into(host_fb.data_ptr())   # warm
     barrier(); r.reset_counters()
+    flatten_ms = []
     t0 = time.perf_counter()
     for i in range(e2e_steps):
+        scene.set_world_bvh(pkg.WORLD_BVH_QUALITY)  # bumps the scene's version: the renderer must flatten it again (graph walk, SAH build, wide layout)
         r.set_scene(scene)                        # flatten + H2D of the scene arena
+        flatten_ms.append(r.scene_stats()["flatten_ms"])
         step(args.warmup + args.steps + i)
         if rank == 0:
             r.download_into(host_fb.data_ptr())   # resolve + D2H into pinned memory
@@ -255,24 +283,33 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         r.reset_counters(); r.set_profiling(True)
-        s0p = ((args.warmup + args.steps + e2e_steps) * world + rank) * S
-        r.render(W, H, s0p, s0p + S, depth, seed=1984, clear=True, stream=stream)   # rank-local: no collective here
+        a, b = pkg.sample_range(S, rank, world)
+        s0p = (args.warmup + args.steps + e2e_steps) * S
+        r.render(W, H, s0p + a, s0p + b, depth, seed=1984, clear=True, stream=stream)   # rank-local: no collective here
         prof = r.profile(); pc = r.counters(); r.set_profiling(False)
         total_ms = prof.generate_ms + prof.traverse_ms + prof.shade_ms + prof.accumulate_ms + prof.tail_ms + prof.bin_ms
-        ach = ALG_BYTES_PER_RAY_TRAVERSE * pc.rays / (prof.traverse_ms * 1e-3) / 1e9 if prof.traverse_ms > 0 else 0.0
-        traffic = None
-        try:   # DRAM bytes per ray of the kernel from the committed ncu --set full capture, scaled to this run's rays per launch
-            tj = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())["traverse_kernel"]
-            traffic = tj["dram_bytes_per_ray"] * pc.rays / max(1, prof.traverse_launches)
-        except Exception:
-            pass
-        roof = {"bound": "hbm", "kernel": "traverse_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "traffic_note": "bytes per launch = 47.4 B/ray (dram__bytes_read+write of profiles/r1_traverse_ncu.txt) x rays per launch; algorithmic 40 B/ray",
-                "peak_source": peak_src, "algorithmic_bytes_per_ray": ALG_BYTES_PER_RAY_TRAVERSE,
+        trav_s = prof.traverse_ms * 1e-3
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        ncu = load_ncu_profile()
+        nt = (ncu or {}).get("traverse") or {}
+        # The kernel is bound by instruction issue and SIMT lane occupancy (the scene is L1/L2 resident; HBM carries only the
+        # queues).  Work per unit = thread-instructions per ray, from the committed ncu capture of this kernel; time = this
+        # run's CUDA events.  Peak = every lane of every scheduler issuing every cycle at the clock seen during the run.
+        issue_peak = 148 * 4 * 32 * sm_mhz * 1e6 / 1e12
+        tipr = nt.get("thread_inst_per_ray")
+        ach_issue = tipr * pc.rays / trav_s / 1e12 if (tipr and trav_s > 0) else None
+        ach_hbm = ALG_BYTES_PER_RAY_TRAVERSE * pc.rays / trav_s / 1e9 if trav_s > 0 else 0.0
+        roof = {"bound": "issue", "kernel": "traverse_kernel", "achieved": ach_issue, "peak": issue_peak, "unit": "T thread-instructions/s",
+                "frac": ach_issue / issue_peak if ach_issue else None,
+                "traffic": nt.get("dram_bytes_per_ray") * pc.rays / max(1, prof.traverse_launches) if nt.get("dram_bytes_per_ray") else None,
+                "traffic_note": "DRAM bytes per launch = dram__bytes_read+write per ray of the committed ncu capture x this run's rays per launch; algorithmic 40 B/ray",
+                "per_unit": {"thread_instructions_per_ray": tipr, "source": "profiles/r2_ncu.json (sm__inst_executed x smsp__thread_inst_executed_per_inst_executed over every traverse launch of a step / rays)"},
+                "peak_note": f"148 SMs x 4 schedulers x 32 lanes x {sm_mhz:.0f} MHz (clock sampled during the timed region)",
                 "avg_launch_ms": prof.traverse_ms / max(1, prof.traverse_launches), "launches": int(prof.traverse_launches),
-                "note": "traversal is instruction-issue bound with SIMT divergence (scene is L1/L2 resident); HBM carries only the wavefront queues",
-                "issue": {"source": "profiles/r1_traverse_ncu.txt (ncu --set full, static)", "issue_slots_busy_pct": 67, "alu_pipe_busy_pct": 56,
-                          "fma_pipe_busy_pct": 30, "l1_data_pipe_busy_pct": 57, "active_lanes_per_instruction": {"primary_rays": 25.0, "bounce_1": 12.4, "bounce_2": 10.8}}}
+                "ncu": {k: nt.get(k) for k in ("issue_busy_pct", "active_lanes", "warp_inst_per_ray", "l1_hit_pct", "dram_bytes_per_ray")} | {"stale": (ncu or {}).get("stale"), "kernel_sources_commit": (ncu or {}).get("kernel_sources_commit")},
+                "hbm": {"achieved": ach_hbm, "peak": peak, "unit": "GB/s", "frac": ach_hbm / peak, "peak_source": peak_src, "algorithmic_bytes_per_ray": ALG_BYTES_PER_RAY_TRAVERSE,
+                        "note": "the same kernel against the HBM roofline: 32 B ray record read + 8 B hit record written per ray"},
+                "note": "traversal is instruction-issue bound with SIMT divergence: frac = issue-slot utilisation x active lanes / 32"}
         # FP32 work in SURVEY 8(d)'s accounting: 24 flop per box test, 30 per primitive test, 150 per shaded segment, with
         # the box / primitive tests per ray counted live through the rtb_trace_rays hook on this scene's primary rays and
         # one generation of diffuse secondary rays (the mix of a depth-40 path is dominated by the latter).
@@ -288,7 +325,6 @@ def main():
             boxes = 2.0 * ((1 - w_sec) * float(h1["nodes_visited"].mean()) + w_sec * float(h2["nodes_visited"].mean()))
             prims = (1 - w_sec) * float(h1["prims_tested"].mean()) + w_sec * float(h2["prims_tested"].mean())
             flop_per_ray = 24.0 * boxes + 30.0 * prims + 150.0
-            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
             fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
             roof["fp32"] = {"achieved_tflops": flop_per_ray * (rays / world) / (ms * 1e-3) / 1e12, "peak_tflops": fp32_peak, "peak_note": f"148 SMs x 128 lanes x 2 x {sm_mhz:.0f} MHz (non-tensor FP32)",
                             "frac": flop_per_ray * (rays / world) / (ms * 1e-3) / 1e12 / fp32_peak, "box_tests_per_ray": boxes, "prim_tests_per_ray": prims, "flop_per_ray": flop_per_ray,
@@ -298,7 +334,26 @@ def main():
         step_bytes = ALG_BYTES_PER_RAY_STEP * rays + ALG_BYTES_PER_PATH_STEP * paths
         split = {"traverse_ms": prof.traverse_ms, "shade_ms": prof.shade_ms, "generate_ms": prof.generate_ms, "accumulate_ms": prof.accumulate_ms, "tail_ms": prof.tail_ms, "bin_ms": prof.bin_ms,
                  "traverse_share": prof.traverse_ms / total_ms if total_ms else None,
-                 "step_hbm_frac_152B_per_ray": step_bytes / (ms * 1e-3) / 1e9 / peak / max(1, world)}
+                 "step_hbm": {"achieved": step_bytes / (ms * 1e-3) / 1e9 / max(1, world), "peak": peak, "unit": "GB/s per GPU", "frac": step_bytes / (ms * 1e-3) / 1e9 / peak / max(1, world),
+                              "accounting": "SURVEY 8(d): 152 B per ray segment + 32 B per path, whole wavefront, over the timed region"}}
+
+    # ---- once per run: the reduced image of N ranks == one GPU rendering the same sample range (96x96, 16 spp, depth 40)
+    multi_check = None
+    if world > 1:
+        cw = ch = 96; cs = 16
+        a, b = pkg.sample_range(cs, rank, world)
+        r.render(cw, ch, a, b, depth, seed=7, clear=True, stream=stream)
+        red = r.accum_tensor().clone()
+        dist.reduce(red, dst=0)
+        torch.cuda.synchronize()
+        if rank == 0:
+            r.render(cw, ch, 0, cs, depth, seed=7, clear=True, stream=stream); r.synchronize()
+            one = r.download_accum()
+            got = red.cpu().numpy()
+            err = float(np.abs(got[..., :3] - one[..., :3]).max() / max(1.0, float(np.abs(one[..., :3]).max())))
+            multi_check = {"what": f"{cw}x{ch}x{cs} spp split over {world} ranks + NCCL reduce vs the same range on rank 0 alone", "max_rel_err": err,
+                           "sample_counts_equal": bool(np.array_equal(got[..., 3], one[..., 3])), "ok": bool(err < 1e-5 and np.array_equal(got[..., 3], one[..., 3]))}
+        r.render(W, H, 0, 1, depth, seed=1984, clear=True, stream=stream); r.synchronize()      # back to the headline framebuffer size
 
     # ---- CPU baseline + same-stream image check (rank 0, N=1 only)
     cpu = None; psnr_db = None
@@ -337,18 +392,20 @@ def main():
     if rank == 0:
         line = {
             "metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"Book 2 final scene {W}x{H} depth {depth} (BASELINE.json configs[4]); step = {S} spp of every pixel per GPU, "
-                                   f"sample-range partition of the 10000 spp job", "scene": SCENE, "spp_per_step_per_gpu": S,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"Book 2 final scene {W}x{H} depth {depth} (BASELINE.json configs[4]); step = {S} spp of every pixel in total, split over the "
+                                   f"{world} GPU(s) by sample range (the partition of the 10000 spp job)", "scene": SCENE, "spp_per_step": S,
                        "l2": "per-step wavefront queue traffic (~0.15 GB per Mray) is far larger than the 126 MB L2; no flush needed",
                        "rng": "philox4x32-10 keyed (seed,pixel)x(sample,bounce,stream)", "collective": "one NCCL reduce(sum) of the 10.24 MB framebuffer per step" if world > 1 else "none"},
             "paths": {"value": mpaths, "unit": "Mpaths/s"},
             "rays_per_path": rays / paths if paths else None,
             "e2e": {"value": e2e_mrays, "unit": "Mrays/s", "h2d_bytes_per_step": r.scene_bytes(), "d2h_bytes_per_step": W * H * 16,
-                    "what": "rtb_renderer_set_scene (flatten + H2D) + rtb_render + rtb_download (resolve + D2H to pinned host) per step, wall clock"},
+                    "flatten_ms_per_step": sum(flatten_ms) / len(flatten_ms),
+                    "what": "per step, wall clock: rtb_renderer_set_scene of a CHANGED scene (full flatten: graph walk, SAH build, wide layout; then H2D of the arena) "
+                            "+ rtb_render + rtb_download (resolve + D2H into pinned host memory)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": roof, "kernel_split": split,
+            "roofline": roof, "kernel_split": split, "multi_gpu_check": multi_check,
             "cpu_baseline": cpu, "psnr_vs_oracle_db": psnr_db,
             "reference_gpu": refgpu,
         }

@@ -151,16 +151,18 @@ def test_world_bvh_depth_is_bounded_for_degenerate_input(rtb):
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the CPU restatement on the host cores) must print one JSON line with the agreed keys."""
-    import json, subprocess, sys
+    """`bench.py --impl reference` (the CPU restatement on the host cores) must print one JSON line with the agreed keys -
+    and must not need the product's library at all (it renders the committed scene blob): RTB_LIB points nowhere here."""
+    import json, os, subprocess, sys
     out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-spp", "1"],
-                         capture_output=True, text=True, check=True).stdout.strip().splitlines()
+                         capture_output=True, text=True, check=True, env=dict(os.environ, RTB_LIB="/nonexistent/librtb200.so")).stdout.strip().splitlines()
     line = json.loads(out[-1])
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "e2e", "cpu_baseline", "gpu_launches"):
         assert k in line, k
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["vs_baseline"] is None
+    assert line["scaling"] == "strong"
 
 
 def test_obj_mesh_loader(rtb, tmp_path):

@@ -18,7 +18,7 @@ def run(name, steps=6, warmup=3, extra_env=None):
     if name != "default":
         env["RTB_LIB"] = str(ROOT / "ray-tracing-v06_b200" / "variants" / f"librtb200_{name}.so")
     env.update(extra_env or {})
-    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--no-cpu-baseline", "--no-reference-gpu", "--steps", str(steps), "--warmup", str(warmup)],
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--no-cpu-baseline", "--no-reference-gpu", "--spp-per-step", "100", "--steps", str(steps), "--warmup", str(warmup)],
                          capture_output=True, text=True, env=env)
     if out.returncode != 0:
         return {"name": name, "error": out.stderr[-2000:]}

@@ -22,4 +22,4 @@ if __name__ == "__main__":
         r.reset_counters()
         r.render(info.width, info.height, i * a.spp, (i + 1) * a.spp, info.max_depth); r.synchronize()
     c = r.counters()
-    print(f"step {c.render_ms:.2f} ms, {c.rays / c.render_ms / 1e3:.0f} Mrays/s, {c.launches} launches")
+    print(f"step {c.render_ms:.2f} ms, {c.rays / c.render_ms / 1e3:.0f} Mrays/s, {c.launches} launches, rays={c.rays} paths={c.paths} spp={a.spp} scene={a.scene}")
