@@ -52,14 +52,14 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index          # one index, or "0,1,2,..." (one poller for all the GPUs of the run)
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -234,7 +234,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank); sampler.start()      # sampled from the warm-up on, through the timed region
+    sampler = ClockSampler(",".join(str(g) for g in range(world)) if world > 1 else local_rank)
+    if rank == 0:                                                # ONE nvidia-smi poller for all the GPUs of the run (a poller per rank only loads the driver)
+        sampler.start()                                          # sampled from the warm-up on, through the timed region
     for i in range(args.warmup):
         step(i)
     barrier()
@@ -249,6 +251,11 @@ def main():
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     cnt = r.counters()
+    rank_ms = [ms]
+    if world > 1:
+        gathered = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor([ms], dtype=torch.float64, device="cuda"))
+        rank_ms = [float(x.item()) for x in gathered]
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(cnt.rays), float(cnt.paths), float(cnt.launches)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -403,7 +410,7 @@ def main():
                     "flatten_ms_per_step": sum(flatten_ms) / len(flatten_ms),
                     "what": "per step, wall clock: rtb_renderer_set_scene of a CHANGED scene (full flatten: graph walk, SAH build, wide layout; then H2D of the arena) "
                             "+ rtb_render + rtb_download (resolve + D2H into pinned host memory)"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "rank_ms_per_step": [x / args.steps for x in rank_ms], "render_ms_per_step_rank0": cnt.render_ms,
             "clocks": clocks,
             "roofline": roof, "kernel_split": split, "multi_gpu_check": multi_check,
             "cpu_baseline": cpu, "psnr_vs_oracle_db": psnr_db,
