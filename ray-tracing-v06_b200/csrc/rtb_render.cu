@@ -78,7 +78,7 @@ int rtb_renderer_create(rtb_renderer** out, int device) {
 	r->tail_threshold = (uint32_t)r->lc.sms * 768u;   // ~6 warps of rays per SM sub-partition
 	if (const char* e = getenv("RTB_TAIL_THRESHOLD")) r->tail_threshold = (uint32_t)strtoul(e, nullptr, 10);
 	if (const char* e = getenv("RTB_BIN_BITS")) { int a = 0, b = 0; if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 0 && a <= 8 && b >= 0 && b <= 6 && 3 * a + 2 * b <= 26) { r->bin_org_bits = a; r->bin_dir_bits = b; } }
-	if (const char* e = getenv("RTB_BIN_MASK")) r->bin_mask = strtoull(e, nullptr, 16);
+	if (const char* e = getenv("RTB_BIN_MASK")) { r->bin_mask = strtoull(e, nullptr, 16); r->bin_forced = true; }
 	*out = r;
 	return RTB_OK;
 }
@@ -285,7 +285,7 @@ static uint32_t count_tail_checkpoints(uint32_t depth) { uint32_t c = 0; for (ui
 // Which bounces' queues are binned before they are traversed (bit b of the mask), and how finely: RTB_BIN_MASK (hex),
 // RTB_BIN_BITS=<origin bits per axis>,<direction bits per axis> (0,0 = off).
 static bool binned_bounce(const rtb_renderer* r, uint32_t b) {
-	if (r->sv.bin_org_bits + r->sv.bin_dir_bits == 0 || b == 0) return false;
+	if (r->sv.bin_org_bits + r->sv.bin_dir_bits == 0 || b == 0 || !r->bin_on) return false;
 	return b < 64 ? ((r->bin_mask >> b) & 1ull) != 0 : false;
 }
 static uint32_t count_binned_bounces(const rtb_renderer* r, uint32_t depth) { uint32_t c = 0; for (uint32_t b = 1; b < depth; ++b) c += binned_bounce(r, b) ? 1 : 0; return c; }
@@ -341,6 +341,10 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 	rc = ensure_wave(r, (size_t)(npix * S), p->max_depth);
 	if (rc) return rc;
 
+	// Binning pays where walks are long and queues large: a tree of some size (the 20 primitives of a Cornell box are
+	// walked in a few steps whatever the order of the rays: measured 179 vs 157 ms on config 4 with / without) and batches
+	// big enough that the three extra launches per binned bounce are noise.  RTB_BIN_MASK forces the schedule.
+	r->bin_on = r->bin_forced || (r->sv.n_nodes >= 512 && npix * S >= (8ull << 20));
 	BatchParams bp{};
 	bp.width = p->width; bp.height = p->height; bp.row_begin = row_begin; bp.n_rows = row_end - row_begin;
 	bp.npix = (uint32_t)npix; bp.sample_begin = p->sample_begin; bp.sample_end = p->sample_end;
@@ -377,7 +381,7 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 			e = cudaGraphInstantiate(&r->graph_exec, graph, 0);
 			cudaGraphDestroy(graph);
 			if (e != cudaSuccess) return fail(RTB_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
-			r->graph_bp = bp; r->graph_cam = r->cam; r->graph_scene_version = r->scene_version; r->graph_accum = r->d_accum;
+			r->graph_bp = bp; r->graph_bin_on = r->bin_on; r->graph_cam = r->cam; r->graph_scene_version = r->scene_version; r->graph_accum = r->d_accum;
 			r->graph_valid = true;
 		}
 		for (uint32_t b = 0; b < n_batches; ++b) CUDA_TRY(cudaGraphLaunch(r->graph_exec, st));

@@ -60,6 +60,7 @@ struct rtb_renderer {
 	uint64_t launches = 0, batches = 0;
 	int bin_org_bits = 4, bin_dir_bits = 3;                  // ray binning: 2^(3 * 4 + 2 * 3) = 262,144 bins
 	unsigned long long bin_mask = 0x116ull;                   // bounces whose queue is binned before it is traversed (1, 2, 4, 8: the order persists in between)
+	bool bin_on = false, bin_forced = false, graph_bin_on = false;   // binning applies to this render / RTB_BIN_MASK was given / what the cached graph was built with
 	uint32_t tail_threshold = 0;   // live-queue length below which the fused tail kernel takes a batch over
 
 	// optional per-launch event timing (rtb_renderer_set_profiling)
