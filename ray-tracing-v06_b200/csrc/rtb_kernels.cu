@@ -125,7 +125,7 @@ __device__ __forceinline__ uint32_t batch_sample_count(const BatchParams& bp, ui
 
 __global__ void __launch_bounds__(STREAM_THREADS)
 generate_kernel(BatchParams bp, rtb_camera cam, WaveView wv) {
-	const uint32_t batch = *wv.batch_index;
+	const uint32_t batch = bp.batch_base + *wv.batch_index * bp.batch_stride;
 	const uint32_t ns = batch_sample_count(bp, batch);
 	const uint32_t n = ns * bp.npix;
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -588,7 +588,7 @@ traverse_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce, int 
 	const uint32_t n = wv.n_live[bounce];
 	if (n == 0) return;
 	if (blockIdx.x == 0 && threadIdx.x == 0) { RTB_COUNT_CHECKS(n); RTB_CHECK(n <= wv.capacity, RTB_BOUNDS_QUEUE); }
-	const uint32_t batch = *wv.batch_index;
+	const uint32_t batch = bp.batch_base + *wv.batch_index * bp.batch_stride;
 	const int lane = threadIdx.x & 31;
 	const float4* __restrict__ rod = q ? wv.ray_od[1] : wv.ray_od[0];
 	uint32_t* counter = wv.work + 2 * bounce;
@@ -914,7 +914,7 @@ shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce, int q) 
 	if (bounce >= *wv.tail_from) return;
 	const uint32_t n = wv.n_live[bounce];
 	if (n == 0) return;
-	const uint32_t batch = *wv.batch_index;
+	const uint32_t batch = bp.batch_base + *wv.batch_index * bp.batch_stride;
 	const int in = q, out = in ^ 1;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const float4* __restrict__ rod = in ? wv.ray_od[1] : wv.ray_od[0];
@@ -1144,7 +1144,7 @@ tail_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce0, int q, 
 	const uint32_t n = wv.n_live[bounce0];
 	if (n == 0 || n > threshold) return;
 	if (blockIdx.x == 0 && threadIdx.x == 0) *wv.tail_from = bounce0;
-	const uint32_t batch = *wv.batch_index;
+	const uint32_t batch = bp.batch_base + *wv.batch_index * bp.batch_stride;
 	const int in = q;
 	const float4* __restrict__ rod = in ? wv.ray_od[1] : wv.ray_od[0];
 	const float4* __restrict__ rt_ = in ? wv.thr[1] : wv.thr[0];
@@ -1175,7 +1175,7 @@ tail_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce0, int q, 
 
 __global__ void __launch_bounds__(STREAM_THREADS)
 accumulate_kernel(BatchParams bp, WaveView wv, float4* __restrict__ accum, float4* __restrict__ accum2) {
-	const uint32_t batch = *wv.batch_index;
+	const uint32_t batch = bp.batch_base + *wv.batch_index * bp.batch_stride;
 	const uint32_t ns = batch_sample_count(bp, batch);
 	if (ns == 0) return;
 	const uint32_t stride = gridDim.x * blockDim.x;

@@ -45,6 +45,9 @@ struct BatchParams {
 	uint32_t max_depth;
 	uint32_t seed;
 	uint32_t variance;
+	// A render's batches can be dealt to two lanes (two streams with their own queues, so that the thin late bounces of one
+	// batch overlap the full early bounces of the next): the lane's k-th batch is batch_base + k * batch_stride.
+	uint32_t batch_base, batch_stride;
 };
 
 // Wavefront queues, double buffered.  A ray is a 32-byte record (o.xyz, time)(d.xyz, path id bits) - one DRAM sector, so

@@ -41,6 +41,7 @@ static int upload_staged_scene(rtb_renderer* r);
 
 static void free_graph(rtb_renderer* r) {
 	if (r->graph_exec) { cudaGraphExecDestroy(r->graph_exec); r->graph_exec = nullptr; }
+	if (r->graph_exec2) { cudaGraphExecDestroy(r->graph_exec2); r->graph_exec2 = nullptr; }
 	r->graph_valid = false;
 }
 
@@ -77,6 +78,7 @@ int rtb_renderer_create(rtb_renderer** out, int device) {
 	query_occupancy(device, r->lc);
 	r->tail_threshold = (uint32_t)r->lc.sms * 768u;   // ~6 warps of rays per SM sub-partition
 	if (const char* e = getenv("RTB_TAIL_THRESHOLD")) r->tail_threshold = (uint32_t)strtoul(e, nullptr, 10);
+	if (const char* e = getenv("RTB_LANES")) r->lanes = atoi(e) >= 2 ? 2 : 1;
 	if (const char* e = getenv("RTB_BIN_BITS")) { int a = 0, b = 0; if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 0 && a <= 8 && b >= 0 && b <= 6 && 3 * a + 2 * b <= 26) { r->bin_org_bits = a; r->bin_dir_bits = b; } }
 	if (const char* e = getenv("RTB_BIN_MASK")) { r->bin_mask = strtoull(e, nullptr, 16); r->bin_forced = true; }
 	*out = r;
@@ -90,7 +92,10 @@ void rtb_renderer_destroy(rtb_renderer* r) {
 	free_graph(r);
 	free_gpu_scratch(r->build_scratch);
 	for (cudaEvent_t e : r->prof_events) cudaEventDestroy(e);
-	cudaFree(r->d_scene); cudaFree(r->d_accum); cudaFree(r->d_accum2); cudaFree(r->d_out); cudaFree(r->d_wave); cudaFree(r->d_rgb8);
+	if (r->stream2) cudaStreamSynchronize(r->stream2);
+	cudaFree(r->d_scene); cudaFree(r->d_accum); cudaFree(r->d_accum2); cudaFree(r->d_out); cudaFree(r->d_wave); cudaFree(r->d_wave2); cudaFree(r->d_rgb8);
+	for (cudaEvent_t e : {r->ev_lane[0], r->ev_lane[1], r->ev_fork}) if (e) cudaEventDestroy(e);
+	if (r->stream2) cudaStreamDestroy(r->stream2);
 	for (cudaEvent_t e : {r->ev_in, r->ev_out, r->ev_t0, r->ev_t1}) if (e) cudaEventDestroy(e);
 	if (r->stream) cudaStreamDestroy(r->stream);
 	cudaGetLastError();
@@ -240,14 +245,20 @@ static int ensure_framebuffer(rtb_renderer* r, uint32_t w, uint32_t h) {
 	return RTB_OK;
 }
 
-static int ensure_wave(rtb_renderer* r, size_t paths, uint32_t depth) {
-	if (paths <= r->wave_paths && depth <= r->wave_depth && r->d_wave) return RTB_OK;
+// Queues of one lane (0: the renderer's own stream; 1: the second stream multi-batch renders deal every other batch to).
+static int ensure_wave(rtb_renderer* r, int lane, size_t paths, uint32_t depth) {
+	void*& d_wave = lane ? r->d_wave2 : r->d_wave;
+	size_t& wave_paths = lane ? r->wave2_paths : r->wave_paths;
+	uint32_t& wave_depth = lane ? r->wave2_depth : r->wave_depth;
+	WaveView& wv = lane ? r->wv2 : r->wv;
+	if (paths <= wave_paths && depth <= wave_depth && d_wave) return RTB_OK;
 	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	if (r->stream2) CUDA_TRY(cudaStreamSynchronize(r->stream2));
 	free_graph(r);
-	cudaFree(r->d_wave); r->d_wave = nullptr;
-	if (paths < r->wave_paths) paths = r->wave_paths;     // grow-only in both dimensions: alternating sizes do not thrash
-	if (depth < r->wave_depth) depth = r->wave_depth;
-	r->wave_paths = 0; r->wave_depth = 0;
+	cudaFree(d_wave); d_wave = nullptr;
+	if (paths < wave_paths) paths = wave_paths;     // grow-only in both dimensions: alternating sizes do not thrash
+	if (depth < wave_depth) depth = wave_depth;
+	wave_paths = 0; wave_depth = 0;
 	size_t P = align_up(paths, 256);
 	size_t off = 0;
 	auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -257,22 +268,23 @@ static int ensure_wave(rtb_renderer* r, size_t paths, uint32_t depth) {
 	size_t o_tex = take(P * 32), o_ntex = take((depth + 2) * 4);
 	const size_t nbins = (size_t)1 << (3 * r->bin_org_bits + 2 * r->bin_dir_bits);
 	size_t o_bcnt = take(nbins * 4), o_bcur = take(nbins * 4);
-	CUDA_TRY(cudaMalloc(&r->d_wave, off));
-	CUDA_TRY(cudaMemset(r->d_wave, 0, off));
-	uint8_t* b = static_cast<uint8_t*>(r->d_wave);
-	r->wv.ray_od[0] = (float4*)(b + o_od0); r->wv.ray_od[1] = (float4*)(b + o_od1);
-	r->wv.thr[0] = (float4*)(b + o_t0); r->wv.thr[1] = (float4*)(b + o_t1);
-	r->wv.hit = (int2*)(b + o_hit); r->wv.contrib = (float4*)(b + o_con);
-	r->wv.n_live = (uint32_t*)(b + o_live); r->wv.work = (uint32_t*)(b + o_work);
-	r->wv.tex_work = (float4*)(b + o_tex); r->wv.n_tex = (uint32_t*)(b + o_ntex);
-	r->wv.bin_count = (uint32_t*)(b + o_bcnt); r->wv.bin_cursor = (uint32_t*)(b + o_bcur);
-	r->wv.capacity = (uint32_t)P; r->wv.n_bins = (uint32_t)nbins;
-	r->wv.batch_index = (uint32_t*)(b + o_batch); r->wv.tail_from = r->wv.batch_index + 1; r->wv.totals = (unsigned long long*)(b + o_tot);
-	r->wave_paths = P; r->wave_depth = depth;
+	cudaError_t e = cudaMalloc(&d_wave, off);
+	if (e != cudaSuccess) { d_wave = nullptr; cudaGetLastError(); return fail(RTB_ERR_NOMEM, std::string("cudaMalloc of the wavefront queues: ") + cudaGetErrorString(e)); }
+	CUDA_TRY(cudaMemset(d_wave, 0, off));
+	uint8_t* b = static_cast<uint8_t*>(d_wave);
+	wv.ray_od[0] = (float4*)(b + o_od0); wv.ray_od[1] = (float4*)(b + o_od1);
+	wv.thr[0] = (float4*)(b + o_t0); wv.thr[1] = (float4*)(b + o_t1);
+	wv.hit = (int2*)(b + o_hit); wv.contrib = (float4*)(b + o_con);
+	wv.n_live = (uint32_t*)(b + o_live); wv.work = (uint32_t*)(b + o_work);
+	wv.tex_work = (float4*)(b + o_tex); wv.n_tex = (uint32_t*)(b + o_ntex);
+	wv.bin_count = (uint32_t*)(b + o_bcnt); wv.bin_cursor = (uint32_t*)(b + o_bcur);
+	wv.capacity = (uint32_t)P; wv.n_bins = (uint32_t)nbins;
+	wv.batch_index = (uint32_t*)(b + o_batch); wv.tail_from = wv.batch_index + 1; wv.totals = (unsigned long long*)(b + o_tot);
+	wave_paths = P; wave_depth = depth;
 	return RTB_OK;
 }
 
-#define RTB_WAVE_BYTES_PER_PATH 152ull   // 6 x 16 (rays, throughput, double buffered) + 8 (hit) + 16 (contribution) + 32 (texture work list)
+#define RTB_WAVE_BYTES_PER_PATH 152ull   // 2 x (32 ray + 16 throughput), double buffered, + 8 (hit) + 16 (contribution) + 32 (texture work list)
 
 // Bounces before which the fused tail kernel checks whether the live queue has become short.
 static bool tail_checkpoint(uint32_t b) {
@@ -290,20 +302,34 @@ static bool binned_bounce(const rtb_renderer* r, uint32_t b) {
 }
 static uint32_t count_binned_bounces(const rtb_renderer* r, uint32_t depth) { uint32_t c = 0; for (uint32_t b = 1; b < depth; ++b) c += binned_bounce(r, b) ? 1 : 0; return c; }
 
-static void enqueue_batch(rtb_renderer* r, const BatchParams& bp, cudaStream_t st) {
-	prof_begin(r, 0, st); launch_generate(bp, r->cam, r->wv, r->lc, st); prof_end(r, st);
+// One batch of the wavefront on `st` with the queues `wv`.  The accumulation of the batch into the framebuffer is part of it
+// unless the caller orders it itself (two lanes: the accumulations of consecutive batches must not overlap).
+static void enqueue_batch(rtb_renderer* r, const WaveView& wv, const BatchParams& bp, cudaStream_t st, bool with_accumulate) {
+	prof_begin(r, 0, st); launch_generate(bp, r->cam, wv, r->lc, st); prof_end(r, st);
 	int q = 0;   // the queue that holds the rays of bounce b
 	for (uint32_t b = 0; b < bp.max_depth; ++b) {
-		if (r->tail_threshold && tail_checkpoint(b)) { prof_begin(r, 4, st); launch_tail(r->sv, bp, r->wv, b, q, r->tail_threshold, r->lc, st); prof_end(r, st); }
-		prof_begin(r, 1, st); launch_traverse(r->sv, bp, r->wv, b, q, r->lc, st); prof_end(r, st);
+		if (r->tail_threshold && tail_checkpoint(b)) { prof_begin(r, 4, st); launch_tail(r->sv, bp, wv, b, q, r->tail_threshold, r->lc, st); prof_end(r, st); }
+		prof_begin(r, 1, st); launch_traverse(r->sv, bp, wv, b, q, r->lc, st); prof_end(r, st);
 		const bool bin_next = b + 1 < bp.max_depth && binned_bounce(r, b + 1);
-		prof_begin(r, 2, st); launch_shade(r->sv, bp, r->wv, b, q, r->lc, st);
-		if (r->sv.has_deferred_tex && b + 1 < bp.max_depth) launch_texture(r->sv, r->wv, b, q ^ 1, r->lc, st);
+		prof_begin(r, 2, st); launch_shade(r->sv, bp, wv, b, q, r->lc, st);
+		if (r->sv.has_deferred_tex && b + 1 < bp.max_depth) launch_texture(r->sv, wv, b, q ^ 1, r->lc, st);
 		prof_end(r, st);
-		if (bin_next) { prof_begin(r, 5, st); launch_bin_rays(r->sv, r->wv, b + 1, q ^ 1, r->lc, st); prof_end(r, st); }   // ... and back into queue q
+		if (bin_next) { prof_begin(r, 5, st); launch_bin_rays(r->sv, wv, b + 1, q ^ 1, r->lc, st); prof_end(r, st); }   // ... and back into queue q
 		else q ^= 1;
 	}
-	prof_begin(r, 3, st); launch_accumulate(bp, r->wv, r->d_accum, r->d_accum2, r->lc, st); prof_end(r, st);
+	if (with_accumulate) { prof_begin(r, 3, st); launch_accumulate(bp, wv, r->d_accum, r->d_accum2, r->lc, st); prof_end(r, st); }
+}
+
+static int capture_batch_graph(rtb_renderer* r, const WaveView& wv, const BatchParams& bp, cudaStream_t st, bool with_accumulate, cudaGraphExec_t* out) {
+	cudaGraph_t graph = nullptr;
+	CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+	enqueue_batch(r, wv, bp, st, with_accumulate);
+	cudaError_t e = cudaStreamEndCapture(st, &graph);
+	if (e != cudaSuccess) return fail(RTB_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+	e = cudaGraphInstantiate(out, graph, 0);
+	cudaGraphDestroy(graph);
+	if (e != cudaSuccess) return fail(RTB_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+	return RTB_OK;
 }
 
 int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
@@ -338,8 +364,26 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 	if (S > spp) S = spp ? spp : 1;
 	if (!p->samples_per_batch && spp) { uint64_t nb = (spp + S - 1) / S; S = (spp + nb - 1) / nb; }   // equal-sized batches
 	if (npix * S >= (1ull << 31)) return fail(RTB_ERR_INVALID, "rtb_render: batch too large (lower samples_per_batch)");
-	rc = ensure_wave(r, (size_t)(npix * S), p->max_depth);
+	rc = ensure_wave(r, 0, (size_t)(npix * S), p->max_depth);
 	if (rc) return rc;
+	const uint32_t n_batches = spp ? (uint32_t)((spp + S - 1) / S) : 0;
+	const bool use_graph = getenv("RTB_NO_GRAPH") == nullptr && n_batches > 0 && !r->profiling;
+	// Two lanes: every other batch goes to a second stream with queues of its own, so that the thin late bounces of one batch
+	// (a few million rays per launch, tens of launches) overlap the full early bounces of the next.  The accumulations stay in
+	// batch order (events), so the image is bit for bit the one-lane image.  Falls back to one lane when memory is short.
+	bool two_lanes = use_graph && n_batches >= 2 && r->lanes >= 2;
+	if (two_lanes) {
+		if (!r->stream2) {
+			CUDA_TRY(cudaStreamCreateWithFlags(&r->stream2, cudaStreamNonBlocking));
+			for (int k = 0; k < 2; ++k) CUDA_TRY(cudaEventCreateWithFlags(&r->ev_lane[k], cudaEventDisableTiming));
+			CUDA_TRY(cudaEventCreateWithFlags(&r->ev_fork, cudaEventDisableTiming));
+		}
+		if (!(r->d_wave2 && r->wave2_paths >= npix * S && r->wave2_depth >= p->max_depth)) {
+			size_t free_b = 0, total_b = 0;
+			const bool room = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > (size_t)(npix * S) * RTB_WAVE_BYTES_PER_PATH * 5 / 4;
+			if (!room || ensure_wave(r, 1, (size_t)(npix * S), p->max_depth) != RTB_OK) { cudaGetLastError(); two_lanes = false; }
+		}
+	}
 
 	// Binning pays where walks are long and queues large: a tree of some size (the 20 primitives of a Cornell box are
 	// walked in a few steps whatever the order of the rays: measured 179 vs 157 ms on config 4 with / without) and batches
@@ -350,6 +394,7 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 	bp.npix = (uint32_t)npix; bp.sample_begin = p->sample_begin; bp.sample_end = p->sample_end;
 	bp.samples_per_batch = (uint32_t)S; bp.max_depth = p->max_depth; bp.seed = p->seed;
 	bp.variance = (p->flags & RTB_RENDER_VARIANCE) ? 1u : 0u;
+	bp.batch_base = 0; bp.batch_stride = two_lanes ? 2u : 1u;
 
 	cudaStream_t us = static_cast<cudaStream_t>(user_stream);
 	cudaStream_t st = r->stream;
@@ -364,29 +409,43 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 	CUDA_TRY(cudaMemsetAsync(r->wv.batch_index, 0, sizeof(uint32_t), st));
 	CUDA_TRY(cudaEventRecord(r->ev_t0, st));
 
-	const uint32_t n_batches = spp ? (uint32_t)((spp + S - 1) / S) : 0;
 	const uint64_t launches_per_batch = 3 + 2ull * bp.max_depth + (r->tail_threshold ? count_tail_checkpoints(bp.max_depth) : 0) +
 	                                    (r->sv.has_deferred_tex ? bp.max_depth - 1 : 0) + 3ull * count_binned_bounces(r, bp.max_depth);
-	const bool use_graph = getenv("RTB_NO_GRAPH") == nullptr && n_batches > 0 && !r->profiling;
 	if (use_graph) {
-		bool reuse = r->graph_valid && memcmp(&r->graph_bp, &bp, sizeof bp) == 0 && memcmp(&r->graph_cam, &r->cam, sizeof r->cam) == 0 &&
-		             r->graph_scene_version == r->scene_version && r->graph_accum == r->d_accum;
+		bool reuse = r->graph_valid && r->graph_bin_on == r->bin_on && memcmp(&r->graph_bp, &bp, sizeof bp) == 0 && memcmp(&r->graph_cam, &r->cam, sizeof r->cam) == 0 &&
+		             r->graph_scene_version == r->scene_version && r->graph_accum == r->d_accum && (!two_lanes || r->graph_exec2);
 		if (!reuse) {
 			free_graph(r);
-			cudaGraph_t graph = nullptr;
-			CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-			enqueue_batch(r, bp, st);
-			cudaError_t e = cudaStreamEndCapture(st, &graph);
-			if (e != cudaSuccess) return fail(RTB_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-			e = cudaGraphInstantiate(&r->graph_exec, graph, 0);
-			cudaGraphDestroy(graph);
-			if (e != cudaSuccess) return fail(RTB_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+			rc = capture_batch_graph(r, r->wv, bp, st, !two_lanes, &r->graph_exec);
+			if (rc) return rc;
+			if (two_lanes) {
+				BatchParams bp1 = bp; bp1.batch_base = 1;
+				rc = capture_batch_graph(r, r->wv2, bp1, r->stream2, false, &r->graph_exec2);
+				if (rc) return rc;
+			}
 			r->graph_bp = bp; r->graph_bin_on = r->bin_on; r->graph_cam = r->cam; r->graph_scene_version = r->scene_version; r->graph_accum = r->d_accum;
 			r->graph_valid = true;
 		}
-		for (uint32_t b = 0; b < n_batches; ++b) CUDA_TRY(cudaGraphLaunch(r->graph_exec, st));
+		if (!two_lanes) {
+			for (uint32_t b = 0; b < n_batches; ++b) CUDA_TRY(cudaGraphLaunch(r->graph_exec, st));
+		} else {
+			BatchParams bpl[2] = {bp, bp}; bpl[1].batch_base = 1;
+			const WaveView* wvl[2] = {&r->wv, &r->wv2};
+			cudaStream_t stl[2] = {st, r->stream2};
+			CUDA_TRY(cudaEventRecord(r->ev_fork, st));                               // lane 1 starts after the clears above
+			CUDA_TRY(cudaStreamWaitEvent(r->stream2, r->ev_fork, 0));
+			CUDA_TRY(cudaMemsetAsync(r->wv2.batch_index, 0, sizeof(uint32_t), r->stream2));
+			for (uint32_t b = 0; b < n_batches; ++b) {
+				const int L = (int)(b & 1u);
+				CUDA_TRY(cudaGraphLaunch(L ? r->graph_exec2 : r->graph_exec, stl[L]));
+				if (b > 0) CUDA_TRY(cudaStreamWaitEvent(stl[L], r->ev_lane[L ^ 1], 0));   // batch b - 1 is in the framebuffer
+				launch_accumulate(bpl[L], *wvl[L], r->d_accum, r->d_accum2, r->lc, stl[L]);
+				CUDA_TRY(cudaEventRecord(r->ev_lane[L], stl[L]));
+			}
+			CUDA_TRY(cudaStreamWaitEvent(st, r->ev_lane[1], 0));                      // join (lane 1 ran at least one batch)
+		}
 	} else {
-		for (uint32_t b = 0; b < n_batches; ++b) enqueue_batch(r, bp, st);
+		for (uint32_t b = 0; b < n_batches; ++b) enqueue_batch(r, r->wv, bp, st, true);
 	}
 	CUDA_TRY(cudaGetLastError());
 	r->launches += launches_per_batch * n_batches;
@@ -524,10 +583,12 @@ int rtb_get_counters(rtb_renderer* r, rtb_counters* out) {
 	memset(out, 0, sizeof *out);
 	CUDA_TRY(cudaSetDevice(r->device));
 	CUDA_TRY(cudaStreamSynchronize(r->stream));
-	if (r->d_wave) {
+	if (r->stream2) CUDA_TRY(cudaStreamSynchronize(r->stream2));
+	for (int lane = 0; lane < 2; ++lane) {
+		if (!(lane ? r->d_wave2 : r->d_wave)) continue;
 		unsigned long long tot[2] = {0, 0};
-		CUDA_TRY(cudaMemcpy(tot, r->wv.totals, sizeof tot, cudaMemcpyDeviceToHost));
-		out->paths = tot[0]; out->rays = tot[1];
+		CUDA_TRY(cudaMemcpy(tot, (lane ? r->wv2 : r->wv).totals, sizeof tot, cudaMemcpyDeviceToHost));
+		out->paths += tot[0]; out->rays += tot[1];
 	}
 	out->launches = r->launches; out->batches = r->batches;
 	if (r->timed) { float ms = 0.0f; if (cudaEventElapsedTime(&ms, r->ev_t0, r->ev_t1) == cudaSuccess) out->render_ms = ms; else cudaGetLastError(); }
@@ -588,7 +649,9 @@ int rtb_reset_counters(rtb_renderer* r) {
 	if (!r) return fail(RTB_ERR_INVALID, "rtb_reset_counters: null renderer");
 	CUDA_TRY(cudaSetDevice(r->device));
 	CUDA_TRY(cudaStreamSynchronize(r->stream));
+	if (r->stream2) CUDA_TRY(cudaStreamSynchronize(r->stream2));
 	if (r->d_wave) CUDA_TRY(cudaMemset(r->wv.totals, 0, 2 * sizeof(unsigned long long)));
+	if (r->d_wave2) CUDA_TRY(cudaMemset(r->wv2.totals, 0, 2 * sizeof(unsigned long long)));
 	r->launches = 0; r->batches = 0;
 	return RTB_OK;
 }

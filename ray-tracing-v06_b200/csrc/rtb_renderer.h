@@ -51,6 +51,13 @@ struct rtb_renderer {
 	void* d_wave = nullptr; size_t wave_paths = 0; uint32_t wave_depth = 0;
 	WaveView wv{};
 	LaunchCfg lc{};
+	// second lane (rtb_render deals the batches of a multi-batch render to two streams): its own queues, stream and graph
+	void* d_wave2 = nullptr; size_t wave2_paths = 0; uint32_t wave2_depth = 0;
+	WaveView wv2{};
+	cudaStream_t stream2 = nullptr;
+	cudaEvent_t ev_lane[2] = {nullptr, nullptr}, ev_fork = nullptr;
+	cudaGraphExec_t graph_exec2 = nullptr;
+	int lanes = 2;                            // RTB_LANES=1 switches the second lane off
 
 	// cached per-batch graph
 	cudaGraphExec_t graph_exec = nullptr;
