@@ -452,6 +452,9 @@ __device__ __forceinline__ float leaf_test(const SceneView& sv, int code, v3 o, 
 #ifndef RTB_ROBUST_SLAB
 #define RTB_ROBUST_SLAB 1
 #endif
+#ifndef RTB_REG_STACK
+#define RTB_REG_STACK 0
+#endif
 #define TRAV_END ((int)0x80000000)
 
 // MEDIA: 0 = the scene has no media; 1 = all of them are in the pre-test list (the walk itself never meets
@@ -497,6 +500,16 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 #endif
 	int cur = sv.root_ref;
 	int sp = 0;
+	// -DRTB_REG_STACK=1 (experiment): the two youngest stack entries live in registers and only older ones spill to shared
+	// memory - the "short stack in registers" of the brief.  Measured on B200 (round 2): see profiles/r2_experiments.md.
+#if RTB_REG_STACK
+	int top0 = 0, top1 = 0;   // top0 = youngest
+#define STACK_PUSH(v) do { if (sp >= 2) stack[(sp - 2) * TRAVERSE_THREADS] = top1; top1 = top0; top0 = (v); ++sp; } while (0)
+#define STACK_POP(dst) do { dst = top0; top0 = top1; --sp; if (sp >= 2) top1 = stack[(sp - 2) * TRAVERSE_THREADS]; } while (0)
+#else
+#define STACK_PUSH(v) do { stack[sp * TRAVERSE_THREADS] = (v); ++sp; } while (0)
+#define STACK_POP(dst) do { --sp; dst = stack[sp * TRAVERSE_THREADS]; } while (0)
+#endif
 	int n_inner = 0, n_leaf = 0;   // STATS only
 	// "while-while" walk: lanes first descend inner nodes together, then test their leaf primitive
 	// together (a leaf reference is negative; TRAV_END marks an exhausted walk).
@@ -549,11 +562,11 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 				const float lk = fmaxf(ltmin, 0.0f), rk = fmaxf(rtmin, 0.0f);
 				const bool sw = lk > rk || (lk == rk && ltmax > rtmax);
 				RTB_CHECK(sp >= 0 && sp < stack_cap, RTB_BOUNDS_STACK);
-				stack[sp * TRAVERSE_THREADS] = sw ? n3.x : n3.y; ++sp;
+				STACK_PUSH(sw ? n3.x : n3.y);
 				cur = sw ? n3.y : n3.x;
 			} else if (hl) cur = n3.x;
 			else if (hr) cur = n3.y;
-			else if (sp > 0) { --sp; cur = stack[sp * TRAVERSE_THREADS]; }
+			else if (sp > 0) { STACK_POP(cur); }
 			else cur = TRAV_END;
 
 #if !TRAV_WHILE_WHILE
@@ -568,11 +581,13 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 			const float t = leaf_test<(MEDIA == 2)>(sv, code, o, d, a, time, mr, tbest, RaySlab{idx, idy, idz, oix, oiy, oiz}, hit_code);
 			if (t < tbest) { tbest = t; best = hit_code; }   // "if (t >= rec.distance) return false"  SphereHittable.cu:58
 			if (sp == 0) break;
-			--sp; cur = stack[sp * TRAVERSE_THREADS];
+			STACK_POP(cur);
 		}
 	}
 	if (STATS) { stats_out[0] = n_inner; stats_out[1] = n_leaf; }
 	tbest_out = tbest; code_out = best;
+#undef STACK_PUSH
+#undef STACK_POP
 }
 
 #ifndef TRAVERSE_MIN_BLOCKS

@@ -198,12 +198,14 @@ static rtbs_object blank_object(int kind, int mat) {
 
 int rtb_add_sphere(rtb_scene* s, const float c[3], float r, int mat) {
 	if (!s || !c || !mat_ok(s, mat)) return fail(RTB_ERR_INVALID, "rtb_add_sphere: bad argument");
+	if (!(std::fabs(r) > 0.0f) || !std::isfinite(r)) return fail(RTB_ERR_INVALID, "rtb_add_sphere: the radius must be finite and non-zero");
 	rtbs_object o = blank_object(RTB_OBJ_SPHERE, mat);
 	o.f[0] = c[0]; o.f[1] = c[1]; o.f[2] = c[2]; o.f[3] = r;
 	return push_object(s, o);
 }
 int rtb_add_moving_sphere(rtb_scene* s, const float c0[3], const float c1[3], float r, int mat) {
 	if (!s || !c0 || !c1 || !mat_ok(s, mat)) return fail(RTB_ERR_INVALID, "rtb_add_moving_sphere: bad argument");
+	if (!(std::fabs(r) > 0.0f) || !std::isfinite(r)) return fail(RTB_ERR_INVALID, "rtb_add_moving_sphere: the radius must be finite and non-zero");
 	rtbs_object o = blank_object(RTB_OBJ_MOVING_SPHERE, mat);
 	o.f[0] = c0[0]; o.f[1] = c0[1]; o.f[2] = c0[2]; o.f[3] = r; o.f[4] = c1[0]; o.f[5] = c1[1]; o.f[6] = c1[2];
 	return push_object(s, o);
@@ -700,7 +702,8 @@ struct Flattener {
 	void emit_sphere(const rtbs_object& o, int id, const Xf& x) {
 		float c[3]; x.point(o.f, c);
 		DevPrim p{};
-		Box3 b; for (int i = 0; i < 3; ++i) { b.mn[i] = c[i] - o.f[3]; b.mx[i] = c[i] + o.f[3]; }
+		const float rad = std::fabs(o.f[3]);   // (a negative radius - the book's hollow glass ball - turns the normal inside out, not the box)
+		Box3 b; for (int i = 0; i < 3; ++i) { b.mn[i] = c[i] - rad; b.mx[i] = c[i] + rad; }
 		if (is_identity(x)) {
 			p.q[0] = c[0]; p.q[1] = c[1]; p.q[2] = c[2]; p.q[3] = o.f[3];
 			emit(PRIM_SPHERE, p, b, o.mat, id);
@@ -715,7 +718,8 @@ struct Flattener {
 		DevPrim p{};
 		Box3 b;
 		for (int i = 0; i < 3; ++i) {
-			float a0 = c0[i] - o.f[3], a1 = c1[i] - o.f[3], b0 = c0[i] + o.f[3], b1 = c1[i] + o.f[3];
+			const float rad = std::fabs(o.f[3]);
+			float a0 = c0[i] - rad, a1 = c1[i] - rad, b0 = c0[i] + rad, b1 = c1[i] + rad;
 			b.mn[i] = (a1 < a0) ? a1 : a0; b.mx[i] = (b0 < b1) ? b1 : b0;
 		}
 		if (is_identity(x)) {
@@ -804,7 +808,7 @@ struct Flattener {
 				float c[3]; x.point(o.f, c);
 				DevPrim p{}; p.q[0] = c[0]; p.q[1] = c[1]; p.q[2] = c[2]; p.q[3] = o.f[3]; p.q[4] = med.f[1];
 				p.q[5] = rt::u2f((uint32_t)medium_index);
-				Box3 b; for (int i = 0; i < 3; ++i) { b.mn[i] = c[i] - o.f[3]; b.mx[i] = c[i] + o.f[3]; }
+				Box3 b; for (int i = 0; i < 3; ++i) { b.mn[i] = c[i] - std::fabs(o.f[3]); b.mx[i] = c[i] + std::fabs(o.f[3]); }
 				emit(PRIM_MEDIUM_SPHERE, p, b, med.mat, id);
 				return RTB_OK;
 			}
@@ -965,6 +969,7 @@ int flatten(rtb_scene& s, FlatScene& out, const GpuBuildContext* gpu) {
 			for (int k = 0; k < it.nrec; ++k) { out.prims[slot_of[i] + k] = fl.recs[it.first + k]; out.prim_info[slot_of[i] + k] = it.info; out.prim_type[slot_of[i] + k] = fl.rec_type[it.first + k]; }
 		}
 	});
+	if (out.prims.size() >= (1u << (31 - RTB_LEAF_TYPE_BITS))) return fail(RTB_ERR_UNSUPPORTED, "too many primitive record slots for a leaf reference (2^27)");
 	lap("layout");
 
 	// Wide layout: one 64-byte record per inner node carrying both children's boxes, numbered in

@@ -13,6 +13,8 @@
 #include "rt_engine/geometry/Scenes.h"
 
 #include <cmath>
+#include <cstdlib>
+#include <unistd.h>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -411,9 +413,13 @@ std::string write_icosphere_obj(int subdivisions) {
 		}
 		f.swap(nf);
 	}
-	std::string path = "/tmp/rtb_icosphere_" + std::to_string(subdivisions) + ".obj";
-	FILE* o = fopen(path.c_str(), "w");
-	if (!o) throw std::runtime_error("cannot write " + path);
+	// a private temporary file (several ranks build this scene at the same time): mkstemp, unlinked by the caller after loading
+	char tmpl[] = "/tmp/rtb_icosphere_XXXXXX";
+	const int fd = mkstemp(tmpl);
+	if (fd < 0) throw std::runtime_error("cannot create a temporary file for the icosphere");
+	std::string path = tmpl;
+	FILE* o = fdopen(fd, "w");
+	if (!o) { close(fd); throw std::runtime_error("cannot write " + path); }
 	fprintf(o, "# icosphere, %zu vertices, %zu faces\n", v.size(), f.size() / 3);
 	for (auto& p : v) fprintf(o, "v %.9g %.9g %.9g\n", p.x, p.y, p.z);
 	for (size_t k = 0; k < f.size(); k += 3) fprintf(o, "f %d//%d %d//%d %d//%d\n", f[k] + 1, f[k] + 1, f[k + 1] + 1, f[k + 1] + 1, f[k + 2] + 1, f[k + 2] + 1);
@@ -423,7 +429,9 @@ std::string write_icosphere_obj(int subdivisions) {
 
 void build_mesh_icospheres(rtb_scene_info* info) {
 	Keep k;
-	Mesh mesh = MeshHandle::LoadObj(write_icosphere_obj(3));
+	const std::string obj = write_icosphere_obj(3);
+	Mesh mesh = MeshHandle::LoadObj(obj);
+	unlink(obj.c_str());
 	auto even = k.tex(new solid_texture(glm::vec3(.2f, .3f, .1f)));
 	auto odd = k.tex(new solid_texture(glm::vec3(.9f, .9f, .9f)));
 	auto ground = k.mat(new Lambertian(k.tex(new checker_texture(even, odd, 0.8f))));
