@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            # the B200 wavefront path tracer
     python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference on the host cores
 
-A "step" is one pass of the hot path over one batch of synthetic input: `--spp-per-step` samples (800 by
+A "step" is one pass of the hot path over one batch of synthetic input: `--spp-per-step` samples (1600 by
 default) of every pixel of the 800x800 Book 2 final scene, depth 40 - a FIXED total, split over the N ranks
 by sample range (strong scaling: rank r renders samples [r S/N, (r+1) S/N) of the step, exactly the
 partition of the 10,000 spp job), and the per-rank radiance sums are summed onto rank 0 with one NCCL
@@ -145,13 +145,12 @@ def load_ncu_profile():
     if not p.exists():
         return None
     j = json.loads(p.read_text())
-    try:
-        head = subprocess.run(["git", "-C", str(ROOT), "log", "-1", "--format=%H", "--", "ray-tracing-v06_b200/csrc"], capture_output=True, text=True, timeout=10).stdout.strip()
-    except Exception:
-        head = ""
-    j["stale"] = bool(head) and bool(j.get("kernel_sources_commit")) and head != j["kernel_sources_commit"]
-    if not head:
-        j["stale"] = None      # no git history on this box: cannot tell
+    import hashlib
+    h = hashlib.sha1()
+    for f in sorted((ROOT / "ray-tracing-v06_b200" / "csrc").glob("*")):
+        if f.suffix in (".cu", ".h", ".cpp"):
+            h.update(f.name.encode()); h.update(f.read_bytes())
+    j["stale"] = (h.hexdigest() != j.get("kernel_sources_sha1")) if j.get("kernel_sources_sha1") else None
     return j
 
 
@@ -177,7 +176,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--spp-per-step", type=int, default=800, help="samples per pixel per step, ALL GPUs together (split by sample range)")
+    ap.add_argument("--spp-per-step", type=int, default=1600, help="samples per pixel per step, ALL GPUs together (split by sample range)")
     ap.add_argument("--cpu-spp", type=int, default=128, help="samples per pixel of the cpu_baseline sample (rank 0, N=1)")
     ap.add_argument("--ref-spp", type=int, default=16, help="samples per pixel per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -313,7 +312,7 @@ def main():
                 "per_unit": {"thread_instructions_per_ray": tipr, "source": "profiles/r2_ncu.json (sm__inst_executed x smsp__thread_inst_executed_per_inst_executed over every traverse launch of a step / rays)"},
                 "peak_note": f"148 SMs x 4 schedulers x 32 lanes x {sm_mhz:.0f} MHz (clock sampled during the timed region)",
                 "avg_launch_ms": prof.traverse_ms / max(1, prof.traverse_launches), "launches": int(prof.traverse_launches),
-                "ncu": {k: nt.get(k) for k in ("issue_busy_pct", "active_lanes", "warp_inst_per_ray", "l1_hit_pct", "dram_bytes_per_ray")} | {"stale": (ncu or {}).get("stale"), "kernel_sources_commit": (ncu or {}).get("kernel_sources_commit")},
+                "ncu": {k: nt.get(k) for k in ("issue_busy_pct", "active_lanes", "warp_inst_per_ray", "l1_hit_pct", "dram_bytes_per_ray")} | {"stale": (ncu or {}).get("stale"), "kernel_sources_sha1": (ncu or {}).get("kernel_sources_sha1")},
                 "hbm": {"achieved": ach_hbm, "peak": peak, "unit": "GB/s", "frac": ach_hbm / peak, "peak_source": peak_src, "algorithmic_bytes_per_ray": ALG_BYTES_PER_RAY_TRAVERSE,
                         "note": "the same kernel against the HBM roofline: 32 B ray record read + 8 B hit record written per ray"},
                 "note": "traversal is instruction-issue bound with SIMT divergence: frac = issue-slot utilisation x active lanes / 32"}

@@ -103,6 +103,14 @@ __device__ __forceinline__ void st_ray(float4* rec, const float4& o, const float
 	             :: "l"(rec), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w) : "memory");
 }
 
+// What changes from one rtb_render call to the next - the sample range and the seed - is read from device memory, so
+// that the CUDA graph of a batch (whose kernel arguments are frozen at capture) serves every call on the same image size.
+__device__ __forceinline__ BatchParams with_call_params(const BatchParams& in, const WaveView& wv) {
+	BatchParams bp = in;
+	bp.sample_begin = wv.call_params[0]; bp.sample_end = wv.call_params[1]; bp.seed = wv.call_params[2];
+	return bp;
+}
+
 // Path id -> (global pixel index, absolute sample index).  Paths of a batch are laid out
 // sample-major: id = local_sample * npix + local_pixel, local pixels row-major from row_begin.
 __device__ __forceinline__ void path_pixel_sample(const BatchParams& bp, uint32_t batch, uint32_t path,
@@ -124,7 +132,8 @@ __device__ __forceinline__ uint32_t batch_sample_count(const BatchParams& bp, ui
 // generate
 
 __global__ void __launch_bounds__(STREAM_THREADS)
-generate_kernel(BatchParams bp, rtb_camera cam, WaveView wv) {
+generate_kernel(BatchParams bp_in, rtb_camera cam, WaveView wv) {
+	const BatchParams bp = with_call_params(bp_in, wv);
 	const uint32_t batch = bp.batch_base + *wv.batch_index * bp.batch_stride;
 	const uint32_t ns = batch_sample_count(bp, batch);
 	const uint32_t n = ns * bp.npix;
@@ -597,7 +606,8 @@ __device__ __forceinline__ void trace_ray(const SceneView& sv, v3 o, v3 d, float
 // block instead of 16 KB leaves 64 KB more L1 per SM: -2 % on the Book 2 final scene), 32 otherwise.
 template <int MEDIA, int STACK>
 __global__ void __launch_bounds__(TRAVERSE_THREADS, TRAVERSE_MIN_BLOCKS)
-traverse_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce, int q) {
+traverse_kernel(SceneView sv, BatchParams bp_in, WaveView wv, uint32_t bounce, int q) {
+	const BatchParams bp = with_call_params(bp_in, wv);
 	__shared__ int s_stack[STACK * TRAVERSE_THREADS];
 	if (bounce >= *wv.tail_from) return;
 	const uint32_t n = wv.n_live[bounce];
@@ -923,7 +933,8 @@ __device__ __forceinline__ void bin_table_flush(uint32_t* s_key, uint32_t* s_cnt
 #define SHADE_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS)
-shade_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce, int q) {
+shade_kernel(SceneView sv, BatchParams bp_in, WaveView wv, uint32_t bounce, int q) {
+	const BatchParams bp = with_call_params(bp_in, wv);
 	__shared__ uint32_t s_chunk, s_base;
 	__shared__ uint32_t s_warp[SHADE_THREADS / 32];
 	if (bounce >= *wv.tail_from) return;
@@ -1153,7 +1164,8 @@ bin_permute_kernel(SceneView sv, WaveView wv, uint32_t bounce, int q_from) {
 
 template <bool MEDIA, int STACK>
 __global__ void __launch_bounds__(TRAVERSE_THREADS)
-tail_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce0, int q, uint32_t threshold) {
+tail_kernel(SceneView sv, BatchParams bp_in, WaveView wv, uint32_t bounce0, int q, uint32_t threshold) {
+	const BatchParams bp = with_call_params(bp_in, wv);
 	__shared__ int s_stack[STACK * TRAVERSE_THREADS];
 	if (*wv.tail_from < bounce0) return;                 // an earlier checkpoint already took the batch over
 	const uint32_t n = wv.n_live[bounce0];
@@ -1189,7 +1201,8 @@ tail_kernel(SceneView sv, BatchParams bp, WaveView wv, uint32_t bounce0, int q, 
 // accumulate + batch epilogue + resolve
 
 __global__ void __launch_bounds__(STREAM_THREADS)
-accumulate_kernel(BatchParams bp, WaveView wv, float4* __restrict__ accum, float4* __restrict__ accum2) {
+accumulate_kernel(BatchParams bp_in, WaveView wv, float4* __restrict__ accum, float4* __restrict__ accum2) {
+	const BatchParams bp = with_call_params(bp_in, wv);
 	const uint32_t batch = bp.batch_base + *wv.batch_index * bp.batch_stride;
 	const uint32_t ns = batch_sample_count(bp, batch);
 	if (ns == 0) return;
@@ -1213,7 +1226,8 @@ accumulate_kernel(BatchParams bp, WaveView wv, float4* __restrict__ accum, float
 	}
 }
 
-__global__ void end_batch_kernel(BatchParams bp, WaveView wv) {
+__global__ void end_batch_kernel(BatchParams bp_in, WaveView wv) {
+	const BatchParams bp = with_call_params(bp_in, wv);
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
 	unsigned long long rays = 0;
 	for (uint32_t b = 0; b < bp.max_depth; ++b) rays += wv.n_live[b];

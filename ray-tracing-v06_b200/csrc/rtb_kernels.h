@@ -65,6 +65,7 @@ struct WaveView {
 	uint32_t n_bins;
 	uint32_t* bin_count;        // [2^(3 org_bits + 2 dir_bits)] rays of the next queue per bin (zero between uses)
 	uint32_t* bin_cursor;       // same size: where the next ray of each bin goes
+	const uint32_t* call_params; // [4] sample_begin, sample_end, seed of the current rtb_render call (BatchParams carries stale copies in a replayed graph)
 	uint32_t* batch_index;      // device-side batch counter (graph replays need no new arguments)
 	uint32_t* tail_from;        // first bounce handled by the fused tail kernel (0xFFFFFFFF: none yet)
 	unsigned long long* totals; // [0] paths, [1] rays

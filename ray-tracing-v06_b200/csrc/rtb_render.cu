@@ -280,6 +280,7 @@ static int ensure_wave(rtb_renderer* r, int lane, size_t paths, uint32_t depth) 
 	wv.bin_count = (uint32_t*)(b + o_bcnt); wv.bin_cursor = (uint32_t*)(b + o_bcur);
 	wv.capacity = (uint32_t)P; wv.n_bins = (uint32_t)nbins;
 	wv.batch_index = (uint32_t*)(b + o_batch); wv.tail_from = wv.batch_index + 1; wv.totals = (unsigned long long*)(b + o_tot);
+	wv.call_params = wv.batch_index + 8;   // (same 256-byte block)
 	wave_paths = P; wave_depth = depth;
 	return RTB_OK;
 }
@@ -407,12 +408,15 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 		CUDA_TRY(cudaMemsetAsync(r->d_accum2, 0, bytes, st));
 	}
 	CUDA_TRY(cudaMemsetAsync(r->wv.batch_index, 0, sizeof(uint32_t), st));
+	r->call_params[0] = bp.sample_begin; r->call_params[1] = bp.sample_end; r->call_params[2] = bp.seed; r->call_params[3] = 0;
+	CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(r->wv.call_params), r->call_params, sizeof r->call_params, cudaMemcpyHostToDevice, st));   // (pageable source: staged before the call returns)
 	CUDA_TRY(cudaEventRecord(r->ev_t0, st));
 
 	const uint64_t launches_per_batch = 3 + 2ull * bp.max_depth + (r->tail_threshold ? count_tail_checkpoints(bp.max_depth) : 0) +
 	                                    (r->sv.has_deferred_tex ? bp.max_depth - 1 : 0) + 3ull * count_binned_bounces(r, bp.max_depth);
 	if (use_graph) {
-		bool reuse = r->graph_valid && r->graph_bin_on == r->bin_on && memcmp(&r->graph_bp, &bp, sizeof bp) == 0 && memcmp(&r->graph_cam, &r->cam, sizeof r->cam) == 0 &&
+		BatchParams key = bp; key.sample_begin = key.sample_end = key.seed = 0;   // (those three travel through device memory: call_params)
+		bool reuse = r->graph_valid && r->graph_bin_on == r->bin_on && memcmp(&r->graph_bp, &key, sizeof key) == 0 && memcmp(&r->graph_cam, &r->cam, sizeof r->cam) == 0 &&
 		             r->graph_scene_version == r->scene_version && r->graph_accum == r->d_accum && (!two_lanes || r->graph_exec2);
 		if (!reuse) {
 			free_graph(r);
@@ -423,7 +427,7 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 				rc = capture_batch_graph(r, r->wv2, bp1, r->stream2, false, &r->graph_exec2);
 				if (rc) return rc;
 			}
-			r->graph_bp = bp; r->graph_bin_on = r->bin_on; r->graph_cam = r->cam; r->graph_scene_version = r->scene_version; r->graph_accum = r->d_accum;
+			r->graph_bp = key; r->graph_bin_on = r->bin_on; r->graph_cam = r->cam; r->graph_scene_version = r->scene_version; r->graph_accum = r->d_accum;
 			r->graph_valid = true;
 		}
 		if (!two_lanes) {
@@ -435,6 +439,7 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 			CUDA_TRY(cudaEventRecord(r->ev_fork, st));                               // lane 1 starts after the clears above
 			CUDA_TRY(cudaStreamWaitEvent(r->stream2, r->ev_fork, 0));
 			CUDA_TRY(cudaMemsetAsync(r->wv2.batch_index, 0, sizeof(uint32_t), r->stream2));
+			CUDA_TRY(cudaMemcpyAsync(const_cast<uint32_t*>(r->wv2.call_params), r->call_params, sizeof r->call_params, cudaMemcpyHostToDevice, r->stream2));
 			for (uint32_t b = 0; b < n_batches; ++b) {
 				const int L = (int)(b & 1u);
 				CUDA_TRY(cudaGraphLaunch(L ? r->graph_exec2 : r->graph_exec, stl[L]));

@@ -58,6 +58,7 @@ struct rtb_renderer {
 	cudaEvent_t ev_lane[2] = {nullptr, nullptr}, ev_fork = nullptr;
 	cudaGraphExec_t graph_exec2 = nullptr;
 	int lanes = 2;                            // RTB_LANES=1 switches the second lane off
+	uint32_t call_params[4] = {0, 0, 0, 0};   // host copy of WaveView::call_params
 
 	// cached per-batch graph
 	cudaGraphExec_t graph_exec = nullptr;

@@ -48,6 +48,17 @@ def kernel(path):
             i = hdr.index(k); print(f"{k:92s} {units[i]:16s}", [d[i][:14] for d in data])
 
 
+def kernel_sources_sha1(root):
+    """Content hash of the kernel sources (works where there is no git history, e.g. on the GPU box): bench.py compares it
+    with the tree it runs from and says `stale` when the counters were taken on other kernels."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in sorted((root / "ray-tracing-v06_b200" / "csrc").glob("*")):
+        if f.suffix in (".cu", ".h", ".cpp"):
+            h.update(f.name.encode()); h.update(f.read_bytes())
+    return h.hexdigest()
+
+
 CLASSES = [("traverse", "traverse_kernel"), ("shade", "shade_kernel"), ("texture", "texture_kernel"), ("bin_count", "bin_count_kernel"), ("bin_scan", "bin_scan_kernel"),
            ("bin_permute", "bin_permute_kernel"), ("generate", "generate_kernel"), ("accumulate", "accumulate_kernel"), ("tail", "tail_kernel"), ("end_batch", "end_batch_kernel")]
 
@@ -92,6 +103,7 @@ def to_json(csv_path, plain_log):
         out["kernel_sources_commit"] = subprocess.run(["git", "-C", str(root), "log", "-1", "--format=%H", "--", "ray-tracing-v06_b200/csrc"], capture_output=True, text=True).stdout.strip()
     except Exception:
         out["kernel_sources_commit"] = ""
+    out["kernel_sources_sha1"] = kernel_sources_sha1(root)
     print(json.dumps(out, indent=1))
 
 
