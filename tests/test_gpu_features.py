@@ -210,7 +210,7 @@ for name in rtb.scene_names():
     r.synchronize()
 print("REPORT " + json.dumps(r.debug_bounds_report()))
 ''' % (str(ROOT), str(ROOT / "tests"))
-    env = dict(os.environ, RTB_LIB=str(rtb.DEBUG_LIB_PATH))
+    env = dict(os.environ, RTB_LIB=str(rtb.DEBUG_LIB_PATH), RTB_BIN_MASK="116")   # (forced: these renders are too small for the automatic rule to bin them)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     rep = json.loads([l for l in out.stdout.splitlines() if l.startswith("REPORT ")][-1][7:])
@@ -220,3 +220,31 @@ print("REPORT " + json.dumps(r.debug_bounds_report()))
     r0 = rtb.Renderer(0)
     with pytest.raises(rtb.RtbError, match="RTB_DEBUG_BOUNDS"):
         r0.debug_bounds_report()                     # the release library says so instead of reporting zeros
+
+
+@pytest.mark.parametrize("name,W,H,spp,depth", [("book2_final", 160, 160, 9, 40), ("book2_cornell_smoke", 120, 120, 8, 30), ("book2_earth", 160, 90, 6, 20),
+                                                ("mesh_icospheres", 160, 90, 6, 30), ("book2_bouncing", 160, 90, 8, 50)])
+def test_binning_and_lanes_change_nothing(rtb, orc, monkeypatch, name, W, H, spp, depth):
+    """Ray binning (a counting sort of the live queue between bounces) and the second lane (every other batch on another
+    stream) only change which rays share a warp and which kernels overlap: the radiance sums, the sums of squares and the
+    ray counts must be bit for bit those of the plain wavefront - and equal to the oracle's, path for path.  The automatic rule
+    only bins large batches of large scenes, so the schedule is forced here: every bounce from 1 to 8, three batches."""
+    scene = rtb.Scene.named(name); cam = scene.info.camera
+    results = {}
+    for label, mask, lanes in (("plain", "0", "1"), ("binned", "1fe", "1"), ("binned, two lanes", "1fe", "2"), ("sparse schedule, two lanes", "116", "2")):
+        monkeypatch.setenv("RTB_BIN_MASK", mask); monkeypatch.setenv("RTB_LANES", lanes)
+        r = rtb.Renderer(0)                                   # (the switches are read when the renderer is created)
+        r.set_scene(scene); r.set_camera(cam); r.reset_counters()
+        r.render(W, H, 0, spp, depth, seed=21, variance=True, samples_per_batch=(spp + 2) // 3)
+        acc, acc2 = r.download_accum(want_sum2=True); c = r.counters()
+        results[label] = (acc, acc2, int(c.rays), int(c.launches))
+    monkeypatch.delenv("RTB_BIN_MASK"); monkeypatch.delenv("RTB_LANES")
+    plain = results["plain"]
+    for label, got in results.items():
+        assert np.array_equal(got[0], plain[0]) and np.array_equal(got[1], plain[1]), label
+        assert got[2] == plain[2], label
+    assert results["binned"][3] > plain[3]                    # the extra launches really ran
+    ref, _, rays = orc.OracleScene(scene.serialize()).render(cam, W, H, 0, spp, depth, seed=21)
+    diff = np.abs(plain[0][..., :3] - ref[..., :3]).max(axis=2)
+    assert float((diff > 1e-4 * np.maximum(np.abs(ref[..., :3]).max(axis=2), 1.0)).mean()) <= 0.02
+    assert abs(plain[2] - int(rays)) <= 0.002 * rays + 8

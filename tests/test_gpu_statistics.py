@@ -53,11 +53,12 @@ def test_converged_image_statistics(rtb, orc, cfg, name, W, H, depth):
 
 
 def test_headline_config_full_size_same_streams(rtb, orc):
-    """BASELINE configs[4] at its own size (800x800, depth 40), 4 spp, same Philox streams on both sides: at most 1e-4 of
-    the pixels may differ (a path whose branch flips at an edge-on box hit, where the oracle's own bvh_node cull and the
-    product's slab test round differently) and the ray counts agree to 1e-6."""
+    """BASELINE configs[4] at its own size (800x800, depth 40), 16 spp - one batch of 10.2 M paths, large enough for the
+    automatic rule to bin the queue, as in the benchmark - same Philox streams on both sides: at most 1e-4 of the pixels may
+    differ (a path whose branch flips at an edge-on box hit, where the oracle's own bvh_node cull and the product's slab
+    test round differently) and the ray counts agree to 1e-6."""
     scene = rtb.Scene.named("book2_final"); cam = scene.info.camera
-    W, H, D, S = scene.info.width, scene.info.height, scene.info.max_depth, 4
+    W, H, D, S = scene.info.width, scene.info.height, scene.info.max_depth, 16
     assert (W, H, D) == (800, 800, 40)
     r = rtb.Renderer(0); r.set_scene(scene); r.set_camera(cam)
     r.reset_counters(); r.render(W, H, 0, S, D, seed=1984); g = r.download_accum(); cnt = r.counters()
