@@ -25,7 +25,9 @@ using rt::v3;
 #ifndef TRAVERSE_THREADS
 #define TRAVERSE_THREADS 128
 #endif
-#define SHADE_THREADS 256
+#ifndef SHADE_THREADS
+#define SHADE_THREADS 128   // (B200, r2: 64 / 96 / 128 / 256 / 512 threads: shade 9.8 / 10.3 / 10.1 / 10.6 / 11.3 ms per batch, step 36.6-37.0 / 37.1 / 36.7 / 37.0 / 37.6:
+#endif                      //  smaller blocks wait less at the compaction barriers, but interleave the survivors more finely for the next traverse)
 #define STREAM_THREADS 256
 #define DEEP_STACK_SIZE 64
 #ifndef STACK_SIZE
@@ -904,8 +906,12 @@ __device__ __forceinline__ uint32_t ray_bin(const SceneView& sv, const float4& o
 	return key;
 }
 // Shared-memory hash table of (bin, rays) used by the binning kernels (see "binning" below).
+#ifndef BIN_THREADS
 #define BIN_THREADS 256
+#endif
+#ifndef BIN_ITEMS
 #define BIN_ITEMS 4                                  // rays per thread per tile
+#endif
 #define BIN_TILE (BIN_THREADS * BIN_ITEMS)
 #define BIN_SLOTS 2048                               // hash slots per block: at most half full with one tile's keys
 #define BIN_EMPTY 0xFFFFFFFFu
@@ -930,7 +936,7 @@ __device__ __forceinline__ void bin_table_flush(uint32_t* s_key, uint32_t* s_cnt
 }
 
 #ifndef SHADE_MIN_BLOCKS
-#define SHADE_MIN_BLOCKS 4
+#define SHADE_MIN_BLOCKS 8   // 8 x 128 threads x 64 registers = the whole register file (6 / 9 / 10 blocks: 11.7 / 10.9 / 12.4 ms)
 #endif
 __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS)
 shade_kernel(SceneView sv, BatchParams bp_in, WaveView wv, uint32_t bounce, int q) {

@@ -1,7 +1,7 @@
 #!/bin/bash
-# gpurun with retries while the pod answers "busy" (exit 3): tools/gpurun_retry.sh <timeout> '<command>'
+# gpurun with retries while the pod answers "busy" (exit 3): [GPUS=N] tools/gpurun_retry.sh <timeout> '<command>'
 for attempt in $(seq 1 40); do
-  /usr/local/graft/bin/gpurun --timeout "$1" -- "$2"
+  /usr/local/graft/bin/gpurun ${GPUS:+--gpus $GPUS} --timeout "$1" -- "$2"
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi
   sleep 90
