@@ -164,3 +164,158 @@ def check_image_texture_lookup(rtb, render):
     assert (top_left_to_right == want_top and bottom_left_to_right == want_bottom) or \
            (top_left_to_right == want_top[::-1] and bottom_left_to_right == want_bottom[::-1]), (top_left_to_right, bottom_left_to_right)
     np.testing.assert_allclose(cells[1, 8, 0, 8] if top_left_to_right == want_top else cells[1, 8, 3, 8], np.array(img[0, 0], dtype=np.float32) / np.float32(255.0), atol=1e-6)
+
+
+def check_box_faces(rtb, trace):
+    """book box(a, b) = six quads whose own normals point outward.  Axis-parallel rays from outside meet the face they are
+    aimed at: t = the gap, the point on that face, the normal against the ray, front face; a ray from inside meets the far
+    face from behind (normal still reported against the ray, back face); (u, v) run along the face's edge vectors as the book
+    lays them out (front face: u along +x from min.x, v along +y from min.y); rays past an edge miss."""
+    s = rtb.Scene(); m = s.lambertian(tex=s.image(np.full((4, 4, 3), 128, dtype=np.uint8)))
+    a = np.array([-1.0, 2.0, 3.0]); b = np.array([2.0, 4.0, 8.0])
+    s.set_root(s.list([s.box(a, b, m)]))
+    c = a + (b - a) * np.array([0.25, 0.625, 0.375])
+    for axis in range(3):
+        e = np.zeros(3); e[axis] = 1.0
+        for sign in (+1.0, -1.0):
+            o = c.copy(); o[axis] = (b[axis] + 5.0) if sign > 0 else (a[axis] - 5.0)
+            h = trace(s, _rays(rtb, o, -sign * e))
+            want_p = c.copy(); want_p[axis] = b[axis] if sign > 0 else a[axis]
+            assert h["object"][0] >= 0
+            np.testing.assert_allclose(h["t"][0], 5.0, rtol=1e-6)
+            np.testing.assert_allclose(h["p"][0], want_p, atol=1e-5)
+            np.testing.assert_allclose(h["n"][0], sign * e, atol=1e-6)
+            assert h["front_face"][0] == 1
+            # from the inside the same face is met from behind
+            h = trace(s, _rays(rtb, c, sign * e))
+            np.testing.assert_allclose(h["t"][0], abs(want_p[axis] - c[axis]), rtol=1e-6)
+            np.testing.assert_allclose(h["n"][0], -sign * e, atol=1e-6)
+            assert h["front_face"][0] == 0
+    # front face (z = max.z): Q = (min.x, min.y, max.z), u = dx, v = dy
+    h = trace(s, _rays(rtb, [c[0], c[1], 20.0], [0.0, 0.0, -1.0]))
+    np.testing.assert_allclose([h["u"][0], h["v"][0]], [0.25, 0.625], atol=1e-6)
+    # just past every edge of the silhouette seen along -z: nothing
+    for dx, dy in ((-1e-3, 0.5), (1.0 + 1e-3, 0.5), (0.5, -1e-3), (0.5, 1.0 + 1e-3)):
+        o = np.array([a[0] + dx * (b[0] - a[0]), a[1] + dy * (b[1] - a[1]), 20.0])
+        assert trace(s, _rays(rtb, o, [0.0, 0.0, -1.0]))["object"][0] == -1
+
+
+def check_triangle_barycentric(rtb, trace):
+    """triangle(Q, u, v): the half of the parallelogram with alpha >= 0, beta >= 0, alpha + beta <= 1 - same plane
+    arithmetic as the quad, (u, v) = (alpha, beta)."""
+    s = rtb.Scene(); m = s.lambertian(tex=s.image(np.full((4, 4, 3), 128, dtype=np.uint8)))
+    Q = np.array([0.5, -1.0, 2.0]); u = np.array([3.0, 0.0, 1.0]); v = np.array([0.5, 2.0, -0.5])
+    s.set_root(s.list([s.triangle(Q, u, v, m)]))
+    n = np.cross(u, v); n /= np.linalg.norm(n)
+    inside = np.array([[0.25, 0.25], [0.01, 0.01], [0.98, 0.01], [0.01, 0.98], [0.5, 0.499], [0.125, 0.75]])
+    outside = np.array([[0.5, 0.501], [0.75, 0.75], [0.99, 0.02], [-0.01, 0.5], [0.5, -0.01], [1.01, -0.005]])
+    for ab, hit in ((inside, True), (outside, False)):
+        pts = Q + ab[:, :1] * u + ab[:, 1:] * v
+        o = pts + 4.0 * n + np.array([0.2, 0.1, -0.3])
+        h = trace(s, _rays(rtb, o, pts - o))
+        if hit:
+            assert (h["object"] == 0).all()
+            np.testing.assert_allclose(h["t"], 1.0, rtol=2e-6)
+            np.testing.assert_allclose(np.stack([h["u"], h["v"]], 1), ab, atol=3e-6)
+            np.testing.assert_allclose(h["n"], np.broadcast_to(n, (len(pts), 3)), atol=2e-6)
+        else:
+            assert (h["object"] == -1).all()
+
+
+def check_emitter_and_mirror(rtb, render):
+    """book diffuse_light: a path that reaches an emitter ends there with throughput x emitted (no scattering, either side);
+    metal with fuzz 0 (cu_materials.cuh:77-95) multiplies the throughput by its albedo and reflects.  Under a black
+    background, a camera looking straight at a light of radiance E sees exactly E; looking down at a mirror of albedo A
+    under a ceiling of that light, exactly A * E (float32 products); and nothing but black where neither is."""
+    E = np.array([4.0, 2.0, 1.0], dtype=np.float32); A = np.array([0.8, 0.6, 0.4], dtype=np.float32)
+    s = rtb.Scene()
+    light = s.diffuse_light(s.solid(tuple(float(x) for x in E)))
+    s.set_root(s.list([s.quad((-50.0, 5.0, -50.0), (100.0, 0.0, 0.0), (0.0, 0.0, 100.0), light),          # ceiling
+                       s.quad((-1.0, 0.0, -1.0), (2.0, 0.0, 0.0), (0.0, 0.0, 2.0), s.metal(tuple(float(x) for x in A), 0.0))]))
+    s.set_background(rtb.BG_CONSTANT, (0.0, 0.0, 0.0))
+    W = H = 32
+    up = render(s, rtb.make_camera("pinhole", (0.0, 1.0, 0.0), (0.0, 5.0, 0.0), (0.0, 0.0, -1.0), 40.0, 1.0), W, H, 4, 8)
+    np.testing.assert_array_equal(up[..., :3], np.broadcast_to(np.float32(4.0) * E, (H, W, 3)))            # 4 samples of exactly E
+    down = render(s, rtb.make_camera("pinhole", (0.0, 1.0, 0.0), (0.0, 0.0, 0.0), (0.0, 0.0, -1.0), 40.0, 1.0), W, H, 4, 8)
+    # vfov 40 at distance 1: the view is 0.73 wide - entirely on the 2 x 2 mirror
+    want = np.float32(4.0) * (A * E)
+    np.testing.assert_allclose(down[..., :3], np.broadcast_to(want, (H, W, 3)), rtol=3e-7)
+    away = render(s, rtb.make_camera("pinhole", (60.0, 1.0, 0.0), (100.0, 1.0, 0.0), (0.0, 1.0, 0.0), 20.0, 1.0), W, H, 4, 8)
+    assert np.abs(away[..., :3]).max() == 0.0                                                               # past the edge of the ceiling, looking away: black
+
+
+def check_white_furnace(rtb, render):
+    """Energy conservation: under a uniform white sky every material with albedo 1 must return exactly the sky - Lambertian
+    on spheres, quads and boxes (inter-reflections included), dielectric (reflect or refract, attenuation 1), a white
+    isotropic medium.  Every sample is 1 unless its path runs out of depth (black, Renderer.cu:180), which at depth 50 is
+    vanishingly rare for these objects: a convex Lambertian sphere alone gives exactly spp in every pixel."""
+    W = H = 48; spp = 16
+    one = (1.0, 1.0, 1.0)
+    s = rtb.Scene()
+    s.set_root(s.list([s.sphere((0.0, 0.0, 0.0), 1.0, s.lambertian(albedo=one))]))
+    s.set_background(rtb.BG_CONSTANT, one)
+    cam = rtb.make_camera("pinhole", (0.0, 0.5, 4.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 40.0, 1.0)
+    acc = render(s, cam, W, H, spp, 50)
+    np.testing.assert_array_equal(acc[..., :3], np.full((H, W, 3), np.float32(spp)))
+    s = rtb.Scene()
+    white = s.lambertian(albedo=one)
+    ball = s.sphere((1.2, 0.5, 0.0), 0.5, white)
+    s.set_root(s.list([s.quad((-3.0, 0.0, -3.0), (6.0, 0.0, 0.0), (0.0, 0.0, 6.0), white),
+                       s.sphere((-1.2, 0.5, 0.0), 0.5, s.dielectric(1.5)),
+                       s.translate(s.rotate_y(s.box((-0.4, 0.0, -0.4), (0.4, 0.8, 0.4), white), 30.0), (0.0, 0.0, -0.8)),
+                       s.constant_medium(ball, 1.0, s.isotropic(s.solid(one)))]))
+    s.set_background(rtb.BG_CONSTANT, one)
+    cam = rtb.make_camera("pinhole", (0.0, 1.5, 5.0), (0.0, 0.4, 0.0), (0.0, 1.0, 0.0), 40.0, 1.0)
+    acc = render(s, cam, W, H, spp, 50)[..., :3]
+    assert acc.max() <= spp                                                      # no path ever gains energy
+    assert acc.min() >= spp - 1                                                  # at most one depth-out per pixel
+    assert acc.mean() >= spp * (1.0 - 2e-4)
+
+
+def check_beer_lambert(rtb, render):
+    """book constant_medium: the free path is -log(u) / density, so a purely absorbing medium (isotropic albedo 0) of
+    density s transmits exp(-s L) over a chord of length L - through a slab (box boundary, L = thickness) and through the
+    centre of a sphere boundary (L = 2 R)."""
+    black_sky_free = (1.0, 1.0, 1.0)
+    for kind, dens, L in (("slab", 0.25, 4.0), ("ball", 0.4, 3.0)):
+        s = rtb.Scene()
+        black = s.isotropic(s.solid((0.0, 0.0, 0.0)))
+        shell = s.lambertian(albedo=(1.0, 1.0, 1.0))
+        boundary = s.box((-50.0, -50.0, 0.0), (50.0, 50.0, L), shell) if kind == "slab" else s.sphere((0.0, 0.0, 0.0), 0.5 * L, shell)
+        s.set_root(s.list([s.constant_medium(boundary, dens, black)]))
+        s.set_background(rtb.BG_CONSTANT, black_sky_free)
+        # a very narrow view along the axis: every ray crosses (almost exactly) the full chord
+        cam = rtb.make_camera("pinhole", (0.0, 0.0, -10.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 0.2, 1.0)
+        acc = render(s, cam, 32, 32, 256, 8)
+        mean = float((acc[..., 0] / acc[..., 3]).mean())
+        want = math.exp(-dens * L)
+        sigma = math.sqrt(want * (1.0 - want) / (32 * 32 * 256))
+        assert abs(mean - want) < 4.0 * sigma + 1e-4, (kind, mean, want)
+
+
+def check_perlin_lattice(rtb, render):
+    """book noise_texture: 0.5 (1 + sin(scale z + 10 turb(p, 7))) with gradient (Perlin) noise, which vanishes at every
+    lattice point - and so does every octave of the turbulence there (2^k p is a lattice point too).  At integer (x, y, z)
+    the texture is therefore 0.5 (1 + sin(scale z)) whatever the random tables hold; value noise, a phase taken from another
+    axis, or a missing turbulence term all fail this.  White Lambertian quad carrying the texture under a white sky, a view
+    four thousandths of a unit wide centred on the lattice point: every sample returns the texel under it."""
+    scale = 4.0
+    for (x, y, z) in ((3.0, -2.0, 0.0), (-5.0, 7.0, 1.0), (12.0, 4.0, 2.0), (0.0, 0.0, -3.0)):
+        s = rtb.Scene()
+        s.set_root(s.list([s.quad((x - 1.0, y - 1.0, z), (2.0, 0.0, 0.0), (0.0, 2.0, 0.0), s.lambertian(tex=s.noise(scale)))]))
+        s.set_background(rtb.BG_CONSTANT, (1.0, 1.0, 1.0))
+        cam = rtb.make_camera("pinhole", (x, y, z + 10.0), (x, y, z), (0.0, 1.0, 0.0), math.degrees(2.0 * math.atan(0.002 / 10.0)), 1.0)
+        acc = render(s, cam, 4, 4, 4, 2)
+        got = acc[..., :3] / acc[..., 3:4]
+        assert np.ptp(got, axis=2).max() < 1e-6                              # grey
+        want = 0.5 * (1.0 + math.sin(scale * z))
+        # half a view (0.002 units) away from the lattice point each of the 7 octaves is at most ~0.002 |gradient| in: 10 turb < 0.2
+        assert np.abs(got[..., 0] - want).max() < 0.08, (x, y, z, got[..., 0], want)
+    # away from the lattice the turbulence term is there: half-way between lattice points the value differs from the bare sine
+    s = rtb.Scene()
+    s.set_root(s.list([s.quad((-8.0, -8.0, 1.0), (16.0, 0.0, 0.0), (0.0, 16.0, 0.0), s.lambertian(tex=s.noise(scale)))]))
+    s.set_background(rtb.BG_CONSTANT, (1.0, 1.0, 1.0))
+    cam = rtb.make_camera("pinhole", (0.0, 0.0, 11.0), (0.0, 0.0, 1.0), (0.0, 1.0, 0.0), math.degrees(2.0 * math.atan(0.7)), 1.0)
+    acc = render(s, cam, 64, 64, 1, 2)
+    got = acc[..., 0] / acc[..., 3]
+    assert 0.0 <= got.min() and got.max() <= 1.0 and got.std() > 0.1

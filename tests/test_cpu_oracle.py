@@ -303,6 +303,36 @@ def test_analytic_image_texture(rtb, orc):
     analytic.check_image_texture_lookup(rtb, _oracle_render(orc))
 
 
+def test_analytic_box_faces(rtb, orc):
+    import analytic
+    analytic.check_box_faces(rtb, _oracle_trace(rtb, orc))
+
+
+def test_analytic_triangle(rtb, orc):
+    import analytic
+    analytic.check_triangle_barycentric(rtb, _oracle_trace(rtb, orc))
+
+
+def test_analytic_emitter_and_mirror(rtb, orc):
+    import analytic
+    analytic.check_emitter_and_mirror(rtb, _oracle_render(orc))
+
+
+def test_analytic_white_furnace(rtb, orc):
+    import analytic
+    analytic.check_white_furnace(rtb, _oracle_render(orc))
+
+
+def test_analytic_beer_lambert(rtb, orc):
+    import analytic
+    analytic.check_beer_lambert(rtb, _oracle_render(orc))
+
+
+def test_analytic_perlin_lattice(rtb, orc):
+    import analytic
+    analytic.check_perlin_lattice(rtb, _oracle_render(orc))
+
+
 def test_committed_headline_scene_is_current(rtb, orc):
     """tests/golden/book2_final.rtbs + .json (what `bench.py --impl reference` renders without touching the product) is
     what the host mirror builds today, byte for byte, camera included."""

@@ -640,10 +640,17 @@ def _gpu_render(renderer):
 def test_analytic_pins_gpu(rtb, renderer):
     """The hand-derived known answers for the features the reference lacks (quad alpha/beta and (u,v), rotate_y at 90
     degrees, sphere (u,v) at the poles and the seam, the reference's truncating checker at negative coordinates, image
-    texel lookup), through rtb_trace_rays / rtb_render."""
+    texel lookup, box faces, triangle barycentrics, emitter and mirror radiance, the white furnace, Beer-Lambert transmission, Perlin noise at lattice points), through rtb_trace_rays /
+    rtb_render."""
     import analytic
     analytic.check_quad_alpha_beta(rtb, _gpu_trace(renderer))
     analytic.check_rotate_y_quarter_turn(rtb, _gpu_trace(renderer))
     analytic.check_sphere_uv(rtb, _gpu_trace(renderer))
     analytic.check_checker_at_negative_coordinates(rtb, _gpu_trace(renderer), _gpu_render(renderer))
     analytic.check_image_texture_lookup(rtb, _gpu_render(renderer))
+    analytic.check_box_faces(rtb, _gpu_trace(renderer))
+    analytic.check_triangle_barycentric(rtb, _gpu_trace(renderer))
+    analytic.check_emitter_and_mirror(rtb, _gpu_render(renderer))
+    analytic.check_white_furnace(rtb, _gpu_render(renderer))
+    analytic.check_beer_lambert(rtb, _gpu_render(renderer))
+    analytic.check_perlin_lattice(rtb, _gpu_render(renderer))
