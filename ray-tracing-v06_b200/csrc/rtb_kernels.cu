@@ -906,20 +906,31 @@ __device__ __forceinline__ uint32_t ray_bin(const SceneView& sv, const float4& o
 	return key;
 }
 // Shared-memory hash table of (bin, rays) used by the binning kernels (see "binning" below).
+// (B200, r2: tiles of 1,024 / 2,048 / 4,096 rays = 256 / 512 / 1,024 threads x 4: binning 4.75 / 4.05 / 4.17 ms per batch - a global
+// counter is touched once per distinct key of a TILE, so larger tiles send fewer atomics, until one block per SM is too few.)
 #ifndef BIN_THREADS
-#define BIN_THREADS 256
+#define BIN_THREADS 512
 #endif
 #ifndef BIN_ITEMS
 #define BIN_ITEMS 4                                  // rays per thread per tile
 #endif
 #define BIN_TILE (BIN_THREADS * BIN_ITEMS)
-#define BIN_SLOTS 2048                               // hash slots per block: at most half full with one tile's keys
+#ifndef BIN_SLOTS_LOG2
+#define BIN_SLOTS_LOG2 12
+#endif
+#ifndef BIN_MIN_BLOCKS
+#define BIN_MIN_BLOCKS 2                             // 2 x 512 threads x 64 registers
+#endif
+#define BIN_LAUNCH_BOUNDS __launch_bounds__(BIN_THREADS, BIN_MIN_BLOCKS)
+#define BIN_SLOTS (1 << BIN_SLOTS_LOG2)              // hash slots per block: at most half full with one tile's keys
 #define BIN_EMPTY 0xFFFFFFFFu
+#define BIN_COUNT_SMEM (2 * BIN_SLOTS * sizeof(uint32_t))
+#define BIN_PERMUTE_SMEM (3 * BIN_SLOTS * sizeof(uint32_t))
 
 // Finds or claims the slot of `key` and counts one ray in it (linear probing; callers keep the table at most half full).
 // Returns the slot, with the top bit set when this call claimed it.
 __device__ __forceinline__ uint32_t bin_table_add(uint32_t* s_key, uint32_t* s_cnt, uint32_t key) {
-	uint32_t h = (key * 2654435761u) >> (32 - 11);  // Fibonacci hash to log2(BIN_SLOTS) = 11 bits
+	uint32_t h = (key * 2654435761u) >> (32 - BIN_SLOTS_LOG2);  // Fibonacci hash to log2(BIN_SLOTS) bits
 	for (;;) {
 		const uint32_t prev = atomicCAS(s_key + h, BIN_EMPTY, key);
 		if (prev == BIN_EMPTY || prev == key) { atomicAdd(s_cnt + h, 1u); return prev == BIN_EMPTY ? (h | 0x80000000u) : h; }
@@ -1042,9 +1053,10 @@ texture_kernel(SceneView sv, WaveView wv, uint32_t bounce, int q_out) {
 
 // Rays per bin.  A block's counts gather in its table over many tiles and go to the global counters when the table might
 // not hold another tile's keys, and at the end.
-__global__ void __launch_bounds__(BIN_THREADS)
+__global__ void BIN_LAUNCH_BOUNDS
 bin_count_kernel(SceneView sv, WaveView wv, uint32_t bounce, int q) {
-	__shared__ uint32_t s_key[BIN_SLOTS], s_cnt[BIN_SLOTS];
+	extern __shared__ uint32_t s_bin[];                   // BIN_COUNT_SMEM bytes
+	uint32_t* const s_key = s_bin; uint32_t* const s_cnt = s_bin + BIN_SLOTS;
 	__shared__ uint32_t s_used;
 	if (bounce >= *wv.tail_from) return;
 	const uint32_t n = wv.n_live[bounce];
@@ -1114,9 +1126,10 @@ bin_scan_kernel(WaveView wv, uint32_t bounce) {
 	if (b0 + 3u < wv.n_bins) wv.bin_cursor[b0 + 3u] = run;
 }
 
-__global__ void __launch_bounds__(BIN_THREADS)
+__global__ void BIN_LAUNCH_BOUNDS
 bin_permute_kernel(SceneView sv, WaveView wv, uint32_t bounce, int q_from) {
-	__shared__ uint32_t s_key[BIN_SLOTS], s_cnt[BIN_SLOTS], s_base[BIN_SLOTS];
+	extern __shared__ uint32_t s_bin[];                   // BIN_PERMUTE_SMEM bytes
+	uint32_t* const s_key = s_bin; uint32_t* const s_cnt = s_bin + BIN_SLOTS; uint32_t* const s_base = s_bin + 2 * BIN_SLOTS;
 	if (bounce >= *wv.tail_from) return;
 	const uint32_t n = wv.n_live[bounce];
 	if (n == 0) return;
@@ -1357,7 +1370,9 @@ void query_occupancy(int device, LaunchCfg& lc) {
 	lc.blocks_shade = sms * (occ_s > 0 ? occ_s : 1);
 	lc.blocks_stream = sms * (occ_g > 0 ? occ_g : 1);
 	int occ_b = 0;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, bin_permute_kernel, BIN_THREADS, 0);
+	cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIN_COUNT_SMEM);
+	cudaFuncSetAttribute(bin_permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIN_PERMUTE_SMEM);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, bin_permute_kernel, BIN_THREADS, BIN_PERMUTE_SMEM);
 	lc.blocks_bin = sms * (occ_b > 0 ? occ_b : 1);
 }
 
@@ -1397,9 +1412,9 @@ void launch_texture(const SceneView& sv, const WaveView& wv, uint32_t bounce, in
 }
 void launch_bin_rays(const SceneView& sv, const WaveView& wv, uint32_t bounce, int q_from, const LaunchCfg& lc, cudaStream_t st) {
 	const uint32_t nbins = 1u << (3 * sv.bin_org_bits + 2 * sv.bin_dir_bits);
-	bin_count_kernel<<<lc.blocks_bin, BIN_THREADS, 0, st>>>(sv, wv, bounce, q_from);
+	bin_count_kernel<<<lc.blocks_bin, BIN_THREADS, BIN_COUNT_SMEM, st>>>(sv, wv, bounce, q_from);
 	bin_scan_kernel<<<(nbins + BIN_SCAN_PER_BLOCK - 1) / BIN_SCAN_PER_BLOCK, BIN_SCAN_THREADS, 0, st>>>(wv, bounce);
-	bin_permute_kernel<<<lc.blocks_bin, BIN_THREADS, 0, st>>>(sv, wv, bounce, q_from);
+	bin_permute_kernel<<<lc.blocks_bin, BIN_THREADS, BIN_PERMUTE_SMEM, st>>>(sv, wv, bounce, q_from);
 }
 void launch_accumulate(const BatchParams& bp, const WaveView& wv, float4* accum, float4* accum2, const LaunchCfg& lc, cudaStream_t st) {
 	accumulate_kernel<<<lc.blocks_stream, STREAM_THREADS, 0, st>>>(bp, wv, accum, accum2);
