@@ -417,7 +417,10 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 	if (use_graph) {
 		BatchParams key = bp; key.sample_begin = key.sample_end = key.seed = 0;   // (those three travel through device memory: call_params)
 		bool reuse = r->graph_valid && r->graph_bin_on == r->bin_on && memcmp(&r->graph_bp, &key, sizeof key) == 0 && memcmp(&r->graph_cam, &r->cam, sizeof r->cam) == 0 &&
-		             r->graph_scene_version == r->scene_version && r->graph_accum == r->d_accum && (!two_lanes || r->graph_exec2);
+		             memcmp(&r->graph_sv, &r->sv, sizeof r->sv) == 0 && r->graph_accum == r->d_accum && (!two_lanes || r->graph_exec2);
+		// (The kernels see the scene only through the SceneView they are launched with - section pointers and sizes, tree depth, bin
+		// grid - and the memory behind it: a scene that was edited and flattened again into the same layout, an animation step
+		// for instance, needs no new graph.  Round 2 first keyed the graph on a scene version and re-captured ~300 nodes per change.)
 		if (!reuse) {
 			free_graph(r);
 			rc = capture_batch_graph(r, r->wv, bp, st, !two_lanes, &r->graph_exec);
@@ -427,7 +430,7 @@ int rtb_render(rtb_renderer* r, const rtb_render_params* p, void* user_stream) {
 				rc = capture_batch_graph(r, r->wv2, bp1, r->stream2, false, &r->graph_exec2);
 				if (rc) return rc;
 			}
-			r->graph_bp = key; r->graph_bin_on = r->bin_on; r->graph_cam = r->cam; r->graph_scene_version = r->scene_version; r->graph_accum = r->d_accum;
+			r->graph_bp = key; r->graph_bin_on = r->bin_on; r->graph_cam = r->cam; r->graph_sv = r->sv; r->graph_accum = r->d_accum;
 			r->graph_valid = true;
 		}
 		if (!two_lanes) {

@@ -62,7 +62,7 @@ struct rtb_renderer {
 
 	// cached per-batch graph
 	cudaGraphExec_t graph_exec = nullptr;
-	BatchParams graph_bp{}; rtb_camera graph_cam{}; uint64_t graph_scene_version = 0; bool graph_valid = false;
+	BatchParams graph_bp{}; rtb_camera graph_cam{}; SceneView graph_sv{}; bool graph_valid = false;   // what the captured launches were made with
 	float4 *graph_accum = nullptr;
 
 	uint64_t launches = 0, batches = 0;
