@@ -165,6 +165,25 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["scaling"] == "strong"
 
 
+def test_committed_ncu_capture_is_of_these_kernel_sources():
+    """bench.py quotes the work per ray of its roofline (thread-instructions, active lanes, issue utilisation, DRAM bytes)
+    from profiles/r2_ncu.json instead of carrying literals; the file is stamped with a hash of csrc/.  This is the tripwire
+    that keeps the two together: change a kernel and the capture has to be taken again (tools/README.md), or the bench
+    line says `stale: true`."""
+    import importlib.util, sys
+    spec = importlib.util.spec_from_file_location("bench_for_test", ROOT / "bench.py")
+    mod = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.argv = argv
+    prof = mod.load_ncu_profile()
+    assert prof is not None and prof["stale"] is False, "profiles/r2_ncu.json was captured from other kernel sources"
+    for k in ("traverse", "shade", "bin_permute", "bin_count"):
+        assert prof[k]["thread_inst_per_ray"] > 0 and 1.0 <= prof[k]["active_lanes"] <= 32.0
+
+
 def test_obj_mesh_loader(rtb, tmp_path):
     """MeshHandle::LoadObj / MakeMesh (host/rt_engine/geometry/Mesh.cuh): `v` and `f` records, `i/j/k` corners,
     negative indices, polygons fanned into triangles, degenerate faces dropped; one Triangle per face under a BVH."""
